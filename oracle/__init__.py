@@ -1,0 +1,10 @@
+"""CPU parity oracle for the CL4WSIS pseudo-label hot path (TEST INFRASTRUCTURE ONLY).
+
+Importable only from tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs.  The product package
+``cl4wsis_b200`` never imports this.
+"""
+from .oracle import (  # noqa: F401
+    build, pamr, pamr_weights, peak_extract, find_instance_center, group_pixels,
+    get_instance_segmentation, resize_bilinear_ac, num_threads, set_num_threads,
+)

@@ -1,0 +1,184 @@
+"""ctypes front-end of ``cl4_oracle.c`` — numpy in, numpy out.
+
+TEST INFRASTRUCTURE ONLY (see ``cl4_oracle.c`` header).  Parity status: pinned
+against reference-generated fixtures in ``tests/golden`` (``make_golden.py``).
+
+Function names and argument meaning follow the reference:
+  PAMR.forward                -> pamr()                      wss/modules.py:133-152
+  peak_extract                -> peak_extract()              wss/utils.py:3-25
+  find_instance_center        -> find_instance_center()      modules/utils.py:463-502
+  group_pixels                -> group_pixels()              modules/utils.py:505-542
+  get_instance_segmentation   -> get_instance_segmentation() modules/utils.py:545-606 (beta<=0 path)
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libcl4_oracle.so")
+_lib = None
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i32p = ctypes.POINTER(ctypes.c_int)
+_i64p = ctypes.POINTER(ctypes.c_longlong)
+_u8p = ctypes.POINTER(ctypes.c_ubyte)
+
+
+def build(force=False):
+    """Compile ``libcl4_oracle.so`` with the committed Makefile (gcc + OpenMP)."""
+    src = os.path.join(_HERE, "cl4_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-B", "-C", _HERE, "libcl4_oracle.so"])
+    return _SO
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        lib = ctypes.CDLL(_SO)
+        lib.cl4o_num_threads.restype = ctypes.c_int
+        lib.cl4o_set_num_threads.argtypes = [ctypes.c_int]
+        lib.cl4o_resize_bilinear_ac.argtypes = [_f32p, _f32p] + [ctypes.c_int] * 5
+        lib.cl4o_pamr_weights.argtypes = [_f32p, _f32p] + [ctypes.c_int] * 4 + [_i32p, ctypes.c_int]
+        lib.cl4o_pamr.argtypes = [_f32p, _f32p, _f32p] + [ctypes.c_int] * 7 + [_i32p, ctypes.c_int, ctypes.c_int]
+        lib.cl4o_peak_extract.argtypes = [_f32p, _f32p, _i32p, _i32p] + [ctypes.c_int] * 6
+        lib.cl4o_center_nms.argtypes = [_f32p, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        _i64p, ctypes.c_longlong]
+        lib.cl4o_center_nms.restype = ctypes.c_longlong
+        lib.cl4o_group_pixels.argtypes = [_i64p, ctypes.c_int, _f32p, _u8p, _i64p, ctypes.c_int, ctypes.c_int]
+        _lib = lib
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _check(rc, what):
+    if rc < 0:
+        raise RuntimeError(f"oracle {what} failed with code {rc}")
+
+
+def num_threads():
+    return int(_load().cl4o_num_threads())
+
+
+def set_num_threads(n):
+    _load().cl4o_set_num_threads(int(n))
+
+
+def resize_bilinear_ac(x, size):
+    x = _f32(x)
+    h, w = x.shape[-2:]
+    H, W = size
+    out = np.empty(x.shape[:-2] + (H, W), np.float32)
+    planes = int(np.prod(x.shape[:-2], dtype=np.int64))
+    _check(_load().cl4o_resize_bilinear_ac(_ptr(x, _f32p), _ptr(out, _f32p), planes, h, w, H, W), "resize")
+    return out
+
+
+def pamr_weights(x, dilations):
+    x = _f32(x)
+    B, K, H, W = x.shape
+    dil = np.ascontiguousarray(dilations, dtype=np.int32)
+    w = np.empty((B, 8 * len(dil), H, W), np.float32)
+    _check(_load().cl4o_pamr_weights(_ptr(x, _f32p), _ptr(w, _f32p), B, K, H, W, _ptr(dil, _i32p), len(dil)),
+           "pamr_weights")
+    return w
+
+
+def pamr(x, mask, num_iter=10, dilations=(1, 2, 4, 8, 12, 24)):
+    """PAMR(num_iter, dilations).forward(x, mask) -> [B,C,H,W] float32."""
+    x, mask = _f32(x), _f32(mask)
+    B, K, H, W = x.shape
+    Bm, C, h, w = mask.shape
+    if Bm != B:
+        raise ValueError("batch mismatch")
+    dil = np.ascontiguousarray(dilations, dtype=np.int32)
+    out = np.empty((B, C, H, W), np.float32)
+    _check(_load().cl4o_pamr(_ptr(x, _f32p), _ptr(mask, _f32p), _ptr(out, _f32p), B, K, C, H, W, h, w,
+                             _ptr(dil, _i32p), len(dil), int(num_iter)), "pamr")
+    return out
+
+
+def peak_extract(heat, kernel=5, K=25):
+    """-> (scores f32 [B,C,K], ys i32, xs i32), sorted by (score desc, flat index asc)."""
+    heat = _f32(heat)
+    B, C, H, W = heat.shape
+    sc = np.empty((B, C, K), np.float32)
+    ys = np.empty((B, C, K), np.int32)
+    xs = np.empty((B, C, K), np.int32)
+    _check(_load().cl4o_peak_extract(_ptr(heat, _f32p), _ptr(sc, _f32p), _ptr(ys, _i32p), _ptr(xs, _i32p),
+                                     B, C, H, W, int(kernel), int(K)), "peak_extract")
+    return sc, ys, xs
+
+
+def find_instance_center(ctr_hmp, threshold=0.1, nms_kernel=5, top_k=None):
+    """-> int64 [Kc,2] (y,x) in row-major order.  ``top_k`` follows the reference,
+    including its degenerate branch: when Kc >= top_k the reference
+    thresholds the heat-map by a *coordinate* value (modules/utils.py:500-502)."""
+    ctr_hmp = _f32(ctr_hmp)
+    if ctr_hmp.shape[0] != 1:
+        raise ValueError("Only supports inference for batch size = 1")
+    plane = np.squeeze(ctr_hmp)
+    assert plane.ndim == 2, "Something is wrong with center heatmap dimension."
+    H, W = plane.shape
+    plane = np.ascontiguousarray(plane)
+    cap = H * W
+    ctr = np.empty((cap, 2), np.int64)
+    n = _load().cl4o_center_nms(_ptr(plane, _f32p), float(threshold), int(nms_kernel), H, W, _ptr(ctr, _i64p), cap)
+    _check(n, "center_nms")
+    ctr = ctr[:n].copy()
+    if top_k is None or n < top_k:
+        return ctr
+    # degenerate top-k branch: the k-th largest *coordinate* becomes a heat threshold
+    kth = np.sort(ctr.reshape(-1))[::-1][top_k - 1]
+    nms = _nms_plane(plane, threshold, nms_kernel)
+    return np.argwhere(nms > np.float32(kth)).astype(np.int64)
+
+
+def _nms_plane(plane, threshold, nms_kernel):
+    """thresholded + suppressed heat-map (values -1 where not a centre)."""
+    H, W = plane.shape
+    ctr = np.empty((H * W, 2), np.int64)
+    n = _load().cl4o_center_nms(_ptr(plane, _f32p), float(threshold), int(nms_kernel), H, W, _ptr(ctr, _i64p), H * W)
+    out = np.full((H, W), -1.0, np.float32)
+    c = ctr[:n]
+    out[c[:, 0], c[:, 1]] = plane[c[:, 0], c[:, 1]]
+    return out
+
+
+def group_pixels(ctr, offsets, fg=None):
+    """-> int64 [1,H,W], ids in 1..Kc (times fg when given)."""
+    offsets = _f32(offsets)
+    if offsets.shape[0] != 1:
+        raise ValueError("Only supports inference for batch size = 1")
+    ctr = np.ascontiguousarray(ctr, dtype=np.int64)
+    _, _, H, W = offsets.shape
+    ids = np.empty((1, H, W), np.int64)
+    fgp = None
+    if fg is not None:
+        fg = np.ascontiguousarray(np.asarray(fg).reshape(H, W) != 0, dtype=np.uint8)
+        fgp = _ptr(fg, _u8p)
+    _check(_load().cl4o_group_pixels(_ptr(ctr, _i64p), ctr.shape[0], _ptr(offsets, _f32p), fgp,
+                                     _ptr(ids, _i64p), H, W), "group_pixels")
+    return ids
+
+
+def get_instance_segmentation(fg, ctr_hmp, offsets, threshold=0.1, nms_kernel=3, top_k=None, ignore=True, beta=0):
+    """beta <= 0 path of modules/utils.py:545-606 (no centre clustering)."""
+    if beta > 0:
+        raise NotImplementedError("oracle covers the beta<=0 path; cluster_peaks is a 'next' row (SURVEY §8f)")
+    ctr = find_instance_center(ctr_hmp, threshold, nms_kernel, top_k)
+    fg = np.asarray(fg)
+    if ctr.shape[0] == 0:
+        return np.zeros(fg.shape, np.int64) if ignore else fg.astype(np.int64)
+    return group_pixels(ctr, offsets, fg=fg)

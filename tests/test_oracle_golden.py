@@ -1,0 +1,110 @@
+"""Pins the CPU oracle (oracle/cl4_oracle.c) to outputs of the unmodified reference.
+
+Fixtures come from tests/golden/make_golden.py (reference run live in the build
+container).  Tolerances: fp32 PAMR within rtol 1e-5 / atol 1e-7 of the reference
+(the CUDA path is then held to the 1e-4 bar of BASELINE.md against the oracle);
+centres, instance ids and positive peaks bit-exact.
+"""
+import numpy as np
+import pytest
+
+PAMR_CASES = ["pamr_d6", "pamr_d5", "pamr_tiny_d6", "pamr_1iter", "pamr_flat", "pamr_resize", "pamr_c21_64"]
+
+
+@pytest.mark.parametrize("name", PAMR_CASES)
+def test_pamr_matches_reference(golden, oracle, name):
+    x, m, ref = golden[name + "__x"], golden[name + "__mask"], golden[name + "__out"]
+    got = oracle.pamr(x, m, int(golden[name + "__T"]), golden[name + "__dil"].tolist())
+    assert got.shape == ref.shape and got.dtype == np.float32
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-7)
+
+
+def test_pamr_weights_match_reference(golden, oracle):
+    w = oracle.pamr_weights(golden["weights_d6__x"], [1, 2, 4, 8, 12, 24])
+    np.testing.assert_allclose(w, golden["weights_d6__w"], rtol=2e-5, atol=1e-9)
+    np.testing.assert_allclose(w.sum(1), 1.0, rtol=0, atol=1e-5)  # SURVEY §8c ③
+
+
+def test_resize_identity_is_bit_exact(oracle):
+    # SURVEY §8c ①
+    m = np.random.default_rng(0).random((2, 3, 17, 23)).astype(np.float32)
+    assert np.array_equal(oracle.resize_bilinear_ac(m, (17, 23)), m)
+
+
+@pytest.mark.parametrize("name", ["peak_k15", "peak_k5", "peak_k3_neg", "peak_kat8"])
+def test_peak_extract_matches_reference(golden, oracle, name):
+    heat = golden[name + "__heat"]
+    sc, ys, xs = oracle.peak_extract(heat, int(golden[name + "__kernel"]), int(golden[name + "__K"]))
+    rs, ry, rx = golden[name + "__scores"], golden[name + "__ys"], golden[name + "__xs"]
+    assert sc.dtype == np.float32 and ys.dtype == np.int32 and xs.dtype == np.int32  # SURVEY §8c ⑨
+    assert np.array_equal(sc, rs)  # scores (sorted) are exact, fillers included
+    # indices are defined where the score is positive and unique within its (b,c) row
+    for b in range(sc.shape[0]):
+        for c in range(sc.shape[1]):
+            s = rs[b, c]
+            uniq = np.array([(s == v).sum() == 1 for v in s]) & (s != 0)
+            assert np.array_equal(ys[b, c][uniq], ry[b, c][uniq])
+            assert np.array_equal(xs[b, c][uniq], rx[b, c][uniq])
+            # tied scores: same coordinate set
+            for v in np.unique(s[(s != 0) & ~uniq]):
+                a = set(zip(ys[b, c][s == v].tolist(), xs[b, c][s == v].tolist()))
+                r = set(zip(ry[b, c][s == v].tolist(), rx[b, c][s == v].tolist()))
+                assert a == r
+            # every reported location really holds the reported peak score or is a filler
+            assert np.all((heat[b, c][ys[b, c], xs[b, c]] == sc[b, c]) | (sc[b, c] == 0))
+
+
+def test_peak_kat8_values(golden, oracle):
+    # SURVEY §8c ⑧
+    sc, ys, xs = oracle.peak_extract(golden["peak_kat8__heat"], 5, 5)
+    assert sc[0, 0].tolist() == [np.float32(0.9), np.float32(0.8), np.float32(0.8), 0.0, 0.0]
+    assert list(zip(ys[0, 0][:3].tolist(), xs[0, 0][:3].tolist())) == [(5, 7), (20, 3), (20, 25)]
+
+
+def test_find_instance_center_matches_reference(golden, oracle):
+    n = int(golden["center__n"])
+    assert n >= 10
+    for i in range(n):
+        thr, k, topk = golden[f"center_{i}__args"]
+        topk = None if topk < 0 else int(topk)
+        got = oracle.find_instance_center(golden[f"center_{i}__heat"], float(thr), int(k), topk)
+        ref = golden[f"center_{i}__ctr"]
+        assert got.dtype == np.int64 and got.shape == ref.shape, (i, got.shape, ref.shape)
+        assert np.array_equal(got, ref), i
+
+
+def test_find_instance_center_known_answers(oracle):
+    # SURVEY §8c ⑥
+    h = np.zeros((1, 1, 64, 64), np.float32)
+    h[0, 0, 10, 10], h[0, 0, 10, 12], h[0, 0, 40, 40], h[0, 0, 41, 41], h[0, 0, 5, 60] = .9, .8, .5, .5, .05
+    assert oracle.find_instance_center(h, 0.3, 3).tolist() == [[10, 10], [10, 12], [40, 40], [41, 41]]
+    assert oracle.find_instance_center(h, 0.3, 5).tolist() == [[10, 10], [40, 40], [41, 41]]
+    assert oracle.find_instance_center(h, 0.3, 41).tolist() == [[10, 10], [40, 40], [41, 41]]
+    with pytest.raises(ValueError):
+        oracle.find_instance_center(np.zeros((2, 1, 8, 8), np.float32))
+
+
+def test_group_pixels_matches_reference(golden, oracle):
+    n = int(golden["group__n"])
+    for i in range(n):
+        got = oracle.group_pixels(golden[f"group_{i}__ctr"], golden[f"group_{i}__off"])
+        ref = golden[f"group_{i}__ids"]
+        assert got.dtype == np.int64 and got.shape == ref.shape
+        assert np.array_equal(got, ref), (i, int((got != ref).sum()))
+    # SURVEY §8c ⑤
+    ids = oracle.group_pixels(np.array([[1, 2], [1, 4]]), np.zeros((1, 2, 4, 8), np.float32))
+    assert ids[0, 1].tolist() == [1, 1, 1, 1, 2, 2, 2, 2]
+
+
+def test_get_instance_segmentation_beta0_matches_reference(golden, oracle):
+    n = int(golden["inst__n"])
+    seen = 0
+    for i in range(n):
+        thr, k, ignore, beta = golden[f"inst_{i}__args"]
+        if beta > 0:
+            continue
+        got = oracle.get_instance_segmentation(golden[f"inst_{i}__fg"], golden[f"inst_{i}__heat"],
+                                               golden[f"inst_{i}__off"], float(thr), int(k), None, bool(ignore), 0)
+        assert np.array_equal(got, golden[f"inst_{i}__ids"]), i
+        seen += 1
+    assert seen >= 3
