@@ -1,0 +1,37 @@
+"""cl4wsis_b200 — B200-native (sm_100a) pseudo-label hot path of CL4WSIS.
+
+Drop-in mirrors of the reference API for this path (same names and signatures):
+
+    cl4wsis_b200.wss.modules.PAMR                          wss/modules.py:122-152
+    cl4wsis_b200.wss.utils.peak_extract                    wss/utils.py:3-25
+    cl4wsis_b200.modules.utils.find_instance_center        modules/utils.py:463-502
+    cl4wsis_b200.modules.utils.group_pixels                modules/utils.py:505-542
+    cl4wsis_b200.modules.utils.get_instance_segmentation   modules/utils.py:545-606
+
+All compute happens in hand-written CUDA kernels behind the C ABI in
+``include/cl4wsis_b200.h`` (``libcl4wsis_b200.so``); there is no CPU or PyTorch fallback.
+"""
+from . import _lib  # noqa: F401
+from .wss.modules import PAMR  # noqa: F401
+from .wss.utils import peak_extract  # noqa: F401
+from .modules.utils import find_instance_center, get_instance_segmentation, group_pixels  # noqa: F401
+from .pipeline import HostPseudoLabelPipeline, PseudoLabelStep  # noqa: F401
+
+__version__ = "0.1.0"
+
+
+def patch_reference(wss_modules=None, wss_utils=None, modules_utils=None):
+    """Swap the reference's hot-path symbols for this package's in already-imported
+    reference modules.  Pass the reference's ``wss.modules``,
+    ``wss.utils`` and/or ``modules.utils`` module objects."""
+    from .modules import utils as mu
+    from .wss import modules as wm
+    from .wss import utils as wu
+    if wss_modules is not None:
+        wss_modules.PAMR = wm.PAMR
+    if wss_utils is not None:
+        wss_utils.peak_extract = wu.peak_extract
+    if modules_utils is not None:
+        modules_utils.find_instance_center = mu.find_instance_center
+        modules_utils.group_pixels = mu.group_pixels
+        modules_utils.get_instance_segmentation = mu.get_instance_segmentation

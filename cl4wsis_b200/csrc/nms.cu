@@ -1,0 +1,412 @@
+// Max-pool NMS kernels:
+//   * cl4_center_nms   — find_instance_center (reference modules/utils.py:463-502), batched;
+//                        ordered (torch.nonzero / row-major) compaction without atomics.
+//   * cl4_peak_extract — peak_extract (reference wss/utils.py:3-25): NMS + top-K per (b,c) plane
+//                        with a warp-shuffle selection network.
+//
+// Both share one tile routine: a (TH+2r) x (TW+2r) window of the plane is staged in
+// shared memory (outside the image = -inf, ATen's implicit max-pool padding), then a
+// separable k x k maximum is taken (columns, then rows).  The maximum propagates NaN
+// like ATen's max_pool2d.
+#include "common.cuh"
+
+namespace cl4 {
+
+constexpr int kTileW = 64;
+constexpr int kTileH = 32;
+constexpr int kNmsThreads = 256;
+constexpr int kWarpsPerBlock = kNmsThreads / 32;
+
+__host__ __device__ inline int nms_pitch(int r) { return (kTileW + 2 * r) | 1; }  // odd pitch: no bank conflicts
+__host__ inline size_t nms_smem_bytes(int r) {
+    // s_in: (TH+2r) x pitch, s_col: TH x pitch
+    return sizeof(float) * (size_t)nms_pitch(r) * (size_t)(kTileH + 2 * r + kTileH);
+}
+
+// Stage the tile (optionally thresholded: v <= thr -> -1, F.threshold semantics) and
+// leave in s_col[ty][tx + r] ... the k x k window maximum for every tile pixel.
+// Returns through s_in / s_max: centre value at s_in[(ty+r)*pitch + tx+r],
+// pooled value at s_max[ty*pitch + tx].
+template <bool kThreshold>
+__device__ __forceinline__ void tile_maxpool(const float* __restrict__ plane, int H, int W, int y0, int x0, int r,
+                                             float thr, float* s_in, float* s_col) {
+    const int pitch = nms_pitch(r);
+    const int tw = kTileW + 2 * r, th = kTileH + 2 * r;
+    for (int i = threadIdx.x; i < th * tw; i += kNmsThreads) {
+        const int ty = i / tw, tx = i - ty * tw;
+        const int y = y0 + ty - r, x = x0 + tx - r;
+        float v = -INFINITY;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            v = __ldg(plane + (size_t)y * W + x);
+            if (kThreshold) v = (v <= thr) ? -1.f : v;
+        }
+        s_in[ty * pitch + tx] = v;
+    }
+    __syncthreads();
+    // vertical pass: s_col[ty][tx] = max_{j<k} s_in[ty+j][tx], tx over the widened tile
+    for (int i = threadIdx.x; i < kTileH * tw; i += kNmsThreads) {
+        const int ty = i / tw, tx = i - ty * tw;
+        float m = -INFINITY;
+        const float* p = s_in + ty * pitch + tx;
+        for (int j = 0; j <= 2 * r; ++j) m = nanmax(m, p[j * pitch]);
+        s_col[ty * pitch + tx] = m;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float row_window_max(const float* s_col, int pitch, int ty, int tx, int r) {
+    float m = -INFINITY;
+    const float* p = s_col + ty * pitch + tx;
+    for (int j = 0; j <= 2 * r; ++j) m = nanmax(m, p[j]);
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Centre NMS, pass 1: one 32-bit keep-mask word per 32 consecutive x.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNmsThreads)
+center_flags_kernel(const float* __restrict__ heat, float thr, float min_value, int r, int H, int W, int words_per_row,
+                    uint32_t* __restrict__ words) {
+    extern __shared__ float smem[];
+    const int pitch = nms_pitch(r);
+    float* s_in = smem;
+    float* s_col = smem + (size_t)pitch * (kTileH + 2 * r);
+    const int n = blockIdx.z;
+    const int y0 = blockIdx.y * kTileH, x0 = blockIdx.x * kTileW;
+    const float* plane = heat + (size_t)n * H * W;
+    tile_maxpool<true>(plane, H, W, y0, x0, r, thr, s_in, s_col);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // each warp owns rows warp, warp+8, ...; two 32-wide words per row
+    for (int ty = warp; ty < kTileH; ty += kWarpsPerBlock) {
+        const int y = y0 + ty;
+#pragma unroll
+        for (int half = 0; half < kTileW / 32; ++half) {
+            const int tx = half * 32 + lane;
+            const int x = x0 + tx;
+            bool keep = false;
+            if (y < H && x < W) {
+                const float v = s_in[(ty + r) * pitch + tx + r];
+                const float m = row_window_max(s_col, pitch, ty, tx, r);
+                keep = (v == m) && (v > min_value);  // "t != pooled -> -1", then "t > 0" (:485,:492)
+            }
+            const uint32_t word = __ballot_sync(0xffffffffu, keep);
+            const int xw = (x0 >> 5) + half;
+            if (lane == 0 && y < H && xw < words_per_row) words[((size_t)n * H + y) * words_per_row + xw] = word;
+        }
+    }
+}
+
+// Pass 2: one CTA per map.  Row population counts -> exclusive scan -> ordered emit.
+__global__ void __launch_bounds__(1024)
+center_compact_kernel(const uint32_t* __restrict__ words, int H, int words_per_row, long long* __restrict__ ctr_out,
+                      int* __restrict__ count_out, int max_out, int* __restrict__ row_off_scratch) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int n = blockIdx.x;
+    const uint32_t* wn = words + (size_t)n * H * words_per_row;
+    int* row_off = row_off_scratch + (size_t)n * H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    // exclusive scan of per-row counts, blockDim.x rows at a time
+    for (int yb = 0; yb < H; yb += blockDim.x) {
+        const int y = yb + threadIdx.x;
+        int cnt = 0;
+        if (y < H)
+            for (int i = 0; i < words_per_row; ++i) cnt += __popc(wn[(size_t)y * words_per_row + i]);
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int v = (lane < nwarps) ? s_warp[lane] : 0;
+            int vi = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, vi, o);
+                if (lane >= o) vi += t;
+            }
+            s_warp[lane] = vi - v;  // exclusive warp offsets
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        if (y < H) row_off[y] = carry + s_warp[warp] + inc - cnt;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = carry + s_warp[warp] + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) count_out[n] = s_carry;
+    // ordered emit: one warp per row, lanes over words in order
+    long long* out = ctr_out + (size_t)n * max_out * 2;
+    for (int y = warp; y < H; y += nwarps) {
+        int pos = row_off[y];
+        for (int wb = 0; wb < words_per_row; wb += 32) {
+            const int wi = wb + lane;
+            uint32_t word = (wi < words_per_row) ? wn[(size_t)y * words_per_row + wi] : 0u;
+            const int c = __popc(word);
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            int p = pos + inc - c;
+            while (word) {
+                const int b = __ffs(word) - 1;
+                word &= word - 1;
+                if (p < max_out) {
+                    out[2 * (size_t)p] = y;
+                    out[2 * (size_t)p + 1] = wi * 32 + b;
+                }
+                ++p;
+            }
+            pos += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// peak_extract.  Keys are 64-bit: (order-preserving score bits << 32) | ~flat_index, so that a
+// plain unsigned "greater" is (score desc, index asc); NaN sorts above everything like torch.topk
+// and -0.0 is folded onto +0.0 (they compare equal in the reference).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long make_key(float s, uint32_t idx) {
+    uint32_t u;
+    if (s != s) u = 0xffffffffu;
+    else {
+        if (s == 0.f) s = 0.f;  // -0.0 -> +0.0
+        u = __float_as_uint(s);
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    }
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - idx);
+}
+__device__ __forceinline__ float key_score(unsigned long long key) {
+    uint32_t u = (uint32_t)(key >> 32);
+    if (u == 0xffffffffu) return __uint_as_float(0x7fc00000u);
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ uint32_t key_index(unsigned long long key) { return 0xffffffffu - (uint32_t)key; }
+
+// A warp keeps the best 32*KPL keys seen so far, sorted descending; element i lives in
+// register i/32 of lane i%32.  Key 0 is "empty" (no real key is 0: the index part of a
+// real key is >= 1 because idx < 2^32-1).
+template <int KPL>
+struct WarpTopK {
+    unsigned long long k[KPL];
+    unsigned long long thresh;  // current K-th best (0 while the list is not full)
+    int K;
+
+    __device__ __forceinline__ void init(int K_) {
+        K = K_;
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) k[i] = 0ull;
+        thresh = 0ull;
+    }
+    __device__ __forceinline__ void insert(unsigned long long x, int lane) {  // x is warp-uniform
+        // position = number of stored keys greater than x
+        int pos = 0;
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) pos += __popc(__ballot_sync(0xffffffffu, k[i] > x));
+#pragma unroll
+        for (int i = KPL - 1; i >= 0; --i) {
+            unsigned long long up = __shfl_up_sync(0xffffffffu, k[i], 1);
+            const unsigned long long prev_last = (i > 0) ? __shfl_sync(0xffffffffu, k[i - 1 < 0 ? 0 : i - 1], 31) : 0ull;
+            if (lane == 0) up = prev_last;
+            const int gi = i * 32 + lane;
+            if (gi == pos) k[i] = x;
+            else if (gi > pos) k[i] = up;
+        }
+        const int last = K - 1;  // the K-th best sits in register last/32 of lane last%32
+        unsigned long long t = 0ull;
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+            const unsigned long long v = __shfl_sync(0xffffffffu, k[i], last & 31);
+            if ((last >> 5) == i) t = v;
+        }
+        thresh = t;
+    }
+    // offer one candidate per lane (0 = none)
+    __device__ __forceinline__ void offer(unsigned long long cand, int lane) {
+        uint32_t m = __ballot_sync(0xffffffffu, cand > thresh);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            const unsigned long long x = __shfl_sync(0xffffffffu, cand, src);
+            if (x > thresh) insert(x, lane);  // warp-uniform branch (thresh and x are uniform)
+            m &= m - 1;
+        }
+    }
+};
+
+// Pass 1: per tile, NMS then the tile's best K keys -> cand[plane][tile][K].
+template <int KPL>
+__global__ void __launch_bounds__(kNmsThreads)
+peak_tile_kernel(const float* __restrict__ heat, int r, int H, int W, int K, int tiles_x, int tiles_per_plane,
+                 unsigned long long* __restrict__ cand) {
+    extern __shared__ float smem[];
+    const int pitch = nms_pitch(r);
+    float* s_in = smem;
+    float* s_col = smem + (size_t)pitch * (kTileH + 2 * r);
+    const int plane_id = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int y0 = (tile / tiles_x) * kTileH, x0 = (tile % tiles_x) * kTileW;
+    const float* plane = heat + (size_t)plane_id * H * W;
+    tile_maxpool<false>(plane, H, W, y0, x0, r, 0.f, s_in, s_col);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpTopK<KPL> top;
+    top.init(K);
+    for (int ty = warp; ty < kTileH; ty += kWarpsPerBlock) {
+        const int y = y0 + ty;
+#pragma unroll
+        for (int half = 0; half < kTileW / 32; ++half) {
+            const int tx = half * 32 + lane;
+            const int x = x0 + tx;
+            unsigned long long key = 0ull;
+            if (y < H && x < W) {
+                const float v = s_in[(ty + r) * pitch + tx + r];
+                const float m = row_window_max(s_col, pitch, ty, tx, r);
+                const float peak = __fmul_rn(v, (m == v) ? 1.f : 0.f);  // heat * keep (wss/utils.py:11-13)
+                key = make_key(peak, (uint32_t)(y * W + x));
+            }
+            top.offer(key, lane);
+        }
+    }
+    // merge the 8 warp lists through shared memory (reuse s_in), then warp 0 reselects
+    __syncthreads();
+    unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem);
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) s_keys[warp * (32 * KPL) + i * 32 + lane] = top.k[i];
+    __syncthreads();
+    if (warp == 0) {
+        WarpTopK<KPL> fin;
+        fin.init(K);
+        for (int i = lane; i < kWarpsPerBlock * 32 * KPL; i += 32) fin.offer(s_keys[i], lane);
+        unsigned long long* dst = cand + ((size_t)plane_id * tiles_per_plane + tile) * K;
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+            const int gi = i * 32 + lane;
+            if (gi < K) dst[gi] = fin.k[i];
+        }
+    }
+}
+
+// Pass 2: one warp per plane merges the tile candidates and writes the sorted result.
+template <int KPL>
+__global__ void __launch_bounds__(32)
+peak_merge_kernel(const unsigned long long* __restrict__ cand, int n_cand, int K, int W, float* __restrict__ scores,
+                  int* __restrict__ ys, int* __restrict__ xs) {
+    const int plane_id = blockIdx.x;
+    const int lane = threadIdx.x;
+    const unsigned long long* src = cand + (size_t)plane_id * n_cand;
+    WarpTopK<KPL> top;
+    top.init(K);
+    for (int i0 = 0; i0 < n_cand; i0 += 32) {
+        const int i = i0 + lane;
+        top.offer(i < n_cand ? src[i] : 0ull, lane);
+    }
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+        const int gi = i * 32 + lane;
+        if (gi < K) {
+            const unsigned long long key = top.k[i];
+            const uint32_t idx = key_index(key);
+            const size_t o = (size_t)plane_id * K + gi;
+            scores[o] = key_score(key);
+            ys[o] = (int)__fdiv_rn((float)idx, (float)W);  // (inds / W).int()  (wss/utils.py:18)
+            xs[o] = (int)(idx % (uint32_t)W);              // inds % W          (wss/utils.py:19)
+        }
+    }
+}
+
+template <int KPL>
+static int launch_peak(const float* heat, float* scores, int* ys, int* xs, unsigned long long* cand, int B, int C,
+                       int H, int W, int r, int K, cudaStream_t s) {
+    const int tiles_x = ceil_div(W, kTileW), tiles_y = ceil_div(H, kTileH);
+    const int tiles = tiles_x * tiles_y;
+    size_t smem = nms_smem_bytes(r);
+    const size_t need_keys = sizeof(unsigned long long) * kWarpsPerBlock * 32 * KPL;
+    if (smem < need_keys) smem = need_keys;
+    cudaError_t e = cudaFuncSetAttribute(peak_tile_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("peak_extract: smem attribute: %s", cudaGetErrorString(e));
+        return CL4_ECUDA;
+    }
+    peak_tile_kernel<KPL><<<dim3(tiles, B * C), kNmsThreads, smem, s>>>(heat, r, H, W, K, tiles_x, tiles, cand);
+    int rc = check_launch("peak_tile");
+    if (rc != CL4_OK) return rc;
+    peak_merge_kernel<KPL><<<B * C, 32, 0, s>>>(cand, tiles * K, K, W, scores, ys, xs);
+    return check_launch("peak_merge");
+}
+
+}  // namespace cl4
+
+extern "C" size_t cl4_center_nms_scratch_bytes(int N, int H, int W) {
+    if (N <= 0 || H <= 0 || W <= 0) return 0;
+    const size_t words = (size_t)N * H * cl4::ceil_div(W, 32) * sizeof(uint32_t);
+    return cl4::align_up(words, 256) + (size_t)N * H * sizeof(int);
+}
+
+extern "C" int cl4_center_nms(const float* heat, float threshold, float min_value, int kernel, int N, int H, int W,
+                              long long* ctr_out, int* count_out, int max_out, void* scratch, size_t scratch_bytes,
+                              cl4_stream_t stream) {
+    using namespace cl4;
+    CL4_REQUIRE(N >= 0 && H > 0 && W > 0, CL4_EINVAL, "center_nms: bad shape N=%d H=%d W=%d", N, H, W);
+    CL4_REQUIRE(kernel > 0 && (kernel & 1), CL4_EINVAL, "center_nms: nms kernel must be odd and positive, got %d", kernel);
+    CL4_REQUIRE(heat && count_out && (ctr_out || max_out == 0) && max_out >= 0, CL4_EINVAL, "center_nms: null pointer");
+    CL4_REQUIRE(N <= 65535, CL4_EUNSUPPORTED, "center_nms: N=%d > 65535", N);
+    const int r = (kernel - 1) / 2;
+    const size_t smem = nms_smem_bytes(r);
+    CL4_REQUIRE(smem <= 227 * 1024, CL4_EUNSUPPORTED, "center_nms: nms kernel %d too large for the tile", kernel);
+    CL4_REQUIRE(scratch && scratch_bytes >= cl4_center_nms_scratch_bytes(N, H, W), CL4_ESCRATCH,
+                "center_nms: scratch too small");
+    if (N == 0) return CL4_OK;
+    const int wpr = ceil_div(W, 32);
+    uint32_t* words = reinterpret_cast<uint32_t*>(scratch);
+    int* row_off = reinterpret_cast<int*>(reinterpret_cast<char*>(scratch) +
+                                          align_up((size_t)N * H * wpr * sizeof(uint32_t), 256));
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaFuncSetAttribute(center_flags_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    CL4_REQUIRE(e == cudaSuccess, CL4_ECUDA, "center_nms: smem attribute: %s", cudaGetErrorString(e));
+    dim3 grid(ceil_div(W, kTileW), ceil_div(H, kTileH), N);
+    center_flags_kernel<<<grid, kNmsThreads, smem, s>>>(heat, threshold, min_value, r, H, W, wpr, words);
+    int rc = check_launch("center_flags");
+    if (rc != CL4_OK) return rc;
+    center_compact_kernel<<<N, 1024, 0, s>>>(words, H, wpr, ctr_out, count_out, max_out, row_off);
+    return check_launch("center_compact");
+}
+
+extern "C" size_t cl4_peak_extract_scratch_bytes(int B, int C, int H, int W, int kernel, int K) {
+    (void)kernel;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
+    const size_t tiles = (size_t)cl4::ceil_div(W, cl4::kTileW) * cl4::ceil_div(H, cl4::kTileH);
+    return (size_t)B * C * tiles * K * sizeof(unsigned long long);
+}
+
+extern "C" int cl4_peak_extract(const float* heat, float* scores, int* ys, int* xs, void* scratch, size_t scratch_bytes,
+                                int B, int C, int H, int W, int kernel, int K, cl4_stream_t stream) {
+    using namespace cl4;
+    CL4_REQUIRE(B >= 0 && C >= 0 && H > 0 && W > 0, CL4_EINVAL, "peak_extract: bad shape");
+    CL4_REQUIRE(kernel > 0 && (kernel & 1), CL4_EINVAL, "peak_extract: kernel must be odd and positive, got %d", kernel);
+    CL4_REQUIRE(K >= 1 && (long long)K <= (long long)H * W, CL4_EINVAL, "peak_extract: K=%d out of range for %dx%d", K, H, W);
+    CL4_REQUIRE(K <= CL4_MAX_TOPK, CL4_EUNSUPPORTED, "peak_extract: K=%d > %d", K, CL4_MAX_TOPK);
+    CL4_REQUIRE((long long)H * W < 0xffffffffll, CL4_EUNSUPPORTED, "peak_extract: plane too large");
+    CL4_REQUIRE((long long)B * C <= 65535, CL4_EUNSUPPORTED, "peak_extract: B*C > 65535");
+    if (B * C == 0) return CL4_OK;
+    CL4_REQUIRE(heat && scores && ys && xs, CL4_EINVAL, "peak_extract: null pointer");
+    const int r = (kernel - 1) / 2;
+    CL4_REQUIRE(nms_smem_bytes(r) <= 227 * 1024, CL4_EUNSUPPORTED, "peak_extract: kernel %d too large", kernel);
+    CL4_REQUIRE(scratch && scratch_bytes >= cl4_peak_extract_scratch_bytes(B, C, H, W, kernel, K), CL4_ESCRATCH,
+                "peak_extract: scratch too small");
+    unsigned long long* cand = reinterpret_cast<unsigned long long*>(scratch);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (K <= 32) return launch_peak<1>(heat, scores, ys, xs, cand, B, C, H, W, r, K, s);
+    if (K <= 64) return launch_peak<2>(heat, scores, ys, xs, cand, B, C, H, W, r, K, s);
+    if (K <= 128) return launch_peak<4>(heat, scores, ys, xs, cand, B, C, H, W, r, K, s);
+    return launch_peak<8>(heat, scores, ys, xs, cand, B, C, H, W, r, K, s);
+}

@@ -1,0 +1,283 @@
+// PAMR — pixel-adaptive mask refinement (reference wss/modules.py:122-152).
+//
+//   w[b,p,y,x]   = softmax_p( mean_k( -|x_k - shift_p x_k| / (1e-8 + 0.1*std_k) ) )      (:141-145)
+//   mask <- sum_p w[b,p] * shift_p(mask[b,c])      num_iter times                         (:147-149)
+//
+// shift_p reads the neighbour at (y + dy*d, x + dx*d) with replicate padding, i.e. clamped
+// coordinates (:57-58); p = dilation_index*8 + tap, taps ordered as in :30-40.
+//
+// Data layout in HBM: image [B,K,H,W], weights [B,P,H,W] (planar per tap so that a warp's
+// read of one tap is one coalesced row segment), masks [B,C,H,W]; all fp32.
+#include "common.cuh"
+
+namespace cl4 {
+
+// ---------------------------------------------------------------------------------------------
+// bilinear resize, align_corners=True (reference wss/modules.py:134)
+// ---------------------------------------------------------------------------------------------
+__global__ void resize_bilinear_ac_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w, int H,
+                                          int W, float sy, float sx) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float* src = in + (size_t)blockIdx.z * h * w;
+    const float fy = __fmul_rn(sy, (float)y), fx = __fmul_rn(sx, (float)x);
+    int y0 = min((int)fy, h - 1), x0 = min((int)fx, w - 1);
+    const int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
+    const float ly1 = fy - (float)y0, ly0 = 1.f - ly1;
+    const float lx1 = fx - (float)x0, lx0 = 1.f - lx1;
+    const float top = __fadd_rn(__fmul_rn(lx0, src[y0 * w + x0]), __fmul_rn(lx1, src[y0 * w + x1]));
+    const float bot = __fadd_rn(__fmul_rn(lx0, src[y1 * w + x0]), __fmul_rn(lx1, src[y1 * w + x1]));
+    out[((size_t)blockIdx.z * H + y) * W + x] = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+}
+
+// ---------------------------------------------------------------------------------------------
+// affinity weights: one thread per pixel.  K image channels are looped (K = 3 in the trainer).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+pamr_weights_kernel(const float* __restrict__ img, float* __restrict__ wts, int K, int H, int W, Dilations dil) {
+    constexpr int P = 8 * D;
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int b = blockIdx.z;
+    if (x >= W || y >= H) return;
+    const size_t HW = (size_t)H * W;
+
+    float logit[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) logit[p] = 0.f;
+
+    for (int k = 0; k < K; ++k) {
+        const float* pl = img + ((size_t)b * K + k) * HW;
+        const float c = __ldg(pl + (size_t)y * W + x);
+        float nb[P];
+        float sum = (float)D * c;  // LocalStDev samples the centre once per dilation (wss/modules.py:92-102)
+#pragma unroll
+        for (int di = 0; di < D; ++di) {
+            const int d = dil.d[di];
+            const int ym = max(y - d, 0), yp = min(y + d, H - 1);
+            const int xm = max(x - d, 0), xp = min(x + d, W - 1);
+            const float* r0 = pl + (size_t)ym * W;
+            const float* r1 = pl + (size_t)y * W;
+            const float* r2 = pl + (size_t)yp * W;
+            nb[di * 8 + 0] = __ldg(r0 + xm); nb[di * 8 + 1] = __ldg(r0 + x); nb[di * 8 + 2] = __ldg(r0 + xp);
+            nb[di * 8 + 3] = __ldg(r1 + xm);                                  nb[di * 8 + 4] = __ldg(r1 + xp);
+            nb[di * 8 + 5] = __ldg(r2 + xm); nb[di * 8 + 6] = __ldg(r2 + x); nb[di * 8 + 7] = __ldg(r2 + xp);
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) sum += nb[p];
+        const float mean = sum * (1.f / (float)(9 * D));
+        // two-pass unbiased variance over the 9*D samples
+        float ss = (float)D * (c - mean) * (c - mean);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const float t = nb[p] - mean;
+            ss = fmaf(t, t, ss);
+        }
+        const float sd = sqrtf(ss / (float)(9 * D - 1));
+        const float den = 1e-8f + 0.1f * sd;
+#pragma unroll
+        for (int p = 0; p < P; ++p) logit[p] += __fdiv_rn(-fabsf(c - nb[p]), den);
+    }
+    float mx = -INFINITY;
+    const float invK = 1.f / (float)K;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        logit[p] = (K == 3) ? __fdiv_rn(logit[p], 3.f) : logit[p] * invK;
+        mx = fmaxf(mx, logit[p]);
+    }
+    float z = 0.f;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        logit[p] = expf(logit[p] - mx);
+        z += logit[p];
+    }
+    float* o = wts + (size_t)b * P * HW + (size_t)y * W + x;
+#pragma unroll
+    for (int p = 0; p < P; ++p) o[(size_t)p * HW] = __fdiv_rn(logit[p], z);
+}
+
+// ---------------------------------------------------------------------------------------------
+// propagation sweep, v1: one thread per pixel, the pixel's 8*D weights and clamped neighbour
+// offsets live in registers and are reused over all C classes; neighbours come through L1.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+pamr_sweep_v1_kernel(const float* __restrict__ wts, const float* __restrict__ min_, float* __restrict__ mout, int C,
+                     int H, int W, Dilations dil) {
+    constexpr int P = 8 * D;
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int b = blockIdx.z;
+    if (x >= W || y >= H) return;
+    const size_t HW = (size_t)H * W;
+
+    float w[P];
+    int off[P];
+    const float* wp = wts + (size_t)b * P * HW + (size_t)y * W + x;
+#pragma unroll
+    for (int p = 0; p < P; ++p) w[p] = __ldg(wp + (size_t)p * HW);
+#pragma unroll
+    for (int di = 0; di < D; ++di) {
+        const int d = dil.d[di];
+        const int ym = max(y - d, 0) * W, y0 = y * W, yp = min(y + d, H - 1) * W;
+        const int xm = max(x - d, 0), xp = min(x + d, W - 1);
+        off[di * 8 + 0] = ym + xm; off[di * 8 + 1] = ym + x; off[di * 8 + 2] = ym + xp;
+        off[di * 8 + 3] = y0 + xm;                             off[di * 8 + 4] = y0 + xp;
+        off[di * 8 + 5] = yp + xm; off[di * 8 + 6] = yp + x; off[di * 8 + 7] = yp + xp;
+    }
+    const float* src = min_ + (size_t)b * C * HW;
+    float* dst = mout + (size_t)b * C * HW + (size_t)y * W + x;
+    for (int c = 0; c < C; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) acc = fmaf(w[p], __ldg(src + off[p]), acc);
+        *dst = acc;
+        src += HW;
+        dst += HW;
+    }
+}
+
+template <template <int> class F, typename... Args>
+static int dispatch_D(int D, Args... args) {
+    switch (D) {
+        case 1: return F<1>::run(args...);
+        case 2: return F<2>::run(args...);
+        case 3: return F<3>::run(args...);
+        case 4: return F<4>::run(args...);
+        case 5: return F<5>::run(args...);
+        case 6: return F<6>::run(args...);
+        case 7: return F<7>::run(args...);
+        case 8: return F<8>::run(args...);
+    }
+    set_error("pamr: number of dilations %d outside 1..%d", D, CL4_MAX_DILATIONS);
+    return CL4_EUNSUPPORTED;
+}
+
+template <int D>
+struct WeightsLauncher {
+    static int run(const float* img, float* w, int B, int K, int H, int W, Dilations dil, cudaStream_t s) {
+        dim3 grid(ceil_div(W, 32), ceil_div(H, 8), B);
+        pamr_weights_kernel<D><<<grid, dim3(32, 8), 0, s>>>(img, w, K, H, W, dil);
+        return check_launch("pamr_weights");
+    }
+};
+
+template <int D>
+struct SweepLauncher {
+    static int run(const float* w, const float* mi, float* mo, int B, int C, int H, int W, Dilations dil,
+                   cudaStream_t s) {
+        dim3 grid(ceil_div(W, 32), ceil_div(H, 8), B);
+        pamr_sweep_v1_kernel<D><<<grid, dim3(32, 8), 0, s>>>(w, mi, mo, C, H, W, dil);
+        return check_launch("pamr_sweep");
+    }
+};
+
+static int make_dilations(const int* dilations, int D, Dilations* out) {
+    CL4_REQUIRE(dilations && D >= 1, CL4_EINVAL, "pamr: need at least one dilation");
+    CL4_REQUIRE(D <= CL4_MAX_DILATIONS, CL4_EUNSUPPORTED, "pamr: %d dilations > %d", D, CL4_MAX_DILATIONS);
+    for (int i = 0; i < CL4_MAX_DILATIONS; ++i) out->d[i] = 1;
+    for (int i = 0; i < D; ++i) {
+        CL4_REQUIRE(dilations[i] >= 1, CL4_EINVAL, "pamr: dilation %d must be >= 1", dilations[i]);
+        out->d[i] = dilations[i];
+    }
+    return CL4_OK;
+}
+
+static int check_plane(const char* what, long long B, int H, int W) {
+    CL4_REQUIRE(B >= 0 && H > 0 && W > 0, CL4_EINVAL, "%s: bad shape", what);
+    CL4_REQUIRE((long long)H * W < (1ll << 30), CL4_EUNSUPPORTED, "%s: plane too large", what);
+    CL4_REQUIRE(B <= 65535, CL4_EUNSUPPORTED, "%s: batch > 65535", what);
+    return CL4_OK;
+}
+
+}  // namespace cl4
+
+extern "C" int cl4_resize_bilinear_ac(const float* in, float* out, int planes, int h, int w, int H, int W,
+                                      cl4_stream_t stream) {
+    using namespace cl4;
+    CL4_REQUIRE(planes >= 0 && h > 0 && w > 0 && H > 0 && W > 0, CL4_EINVAL, "resize: bad shape");
+    CL4_REQUIRE(planes <= 65535, CL4_EUNSUPPORTED, "resize: more than 65535 planes");
+    if (planes == 0) return CL4_OK;
+    CL4_REQUIRE(in && out, CL4_EINVAL, "resize: null pointer");
+    const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
+    const float sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    dim3 grid(ceil_div(W, 32), ceil_div(H, 8), planes);
+    resize_bilinear_ac_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, out, h, w, H, W, sy, sx);
+    return check_launch("resize_bilinear_ac");
+}
+
+extern "C" int cl4_pamr_weights(const float* img, float* w, int B, int K, int H, int W, const int* dilations, int D,
+                                cl4_stream_t stream) {
+    using namespace cl4;
+    int rc = check_plane("pamr_weights", B, H, W);
+    if (rc != CL4_OK) return rc;
+    CL4_REQUIRE(K >= 1, CL4_EINVAL, "pamr_weights: K must be >= 1");
+    Dilations dil;
+    rc = make_dilations(dilations, D, &dil);
+    if (rc != CL4_OK) return rc;
+    if (B == 0) return CL4_OK;
+    CL4_REQUIRE(img && w, CL4_EINVAL, "pamr_weights: null pointer");
+    return dispatch_D<WeightsLauncher>(D, img, w, B, K, H, W, dil, (cudaStream_t)stream);
+}
+
+extern "C" int cl4_pamr_sweep(const float* w, const float* mask_in, float* mask_out, int B, int C, int H, int W,
+                              const int* dilations, int D, cl4_stream_t stream) {
+    using namespace cl4;
+    int rc = check_plane("pamr_sweep", B, H, W);
+    if (rc != CL4_OK) return rc;
+    CL4_REQUIRE(C >= 1, CL4_EINVAL, "pamr_sweep: C must be >= 1");
+    CL4_REQUIRE((long long)C * H * W < (1ll << 31), CL4_EUNSUPPORTED, "pamr_sweep: C*H*W too large");
+    Dilations dil;
+    rc = make_dilations(dilations, D, &dil);
+    if (rc != CL4_OK) return rc;
+    if (B == 0) return CL4_OK;
+    CL4_REQUIRE(w && mask_in && mask_out && mask_in != mask_out, CL4_EINVAL, "pamr_sweep: null or aliased pointers");
+    return dispatch_D<SweepLauncher>(D, w, mask_in, mask_out, B, C, H, W, dil, (cudaStream_t)stream);
+}
+
+extern "C" size_t cl4_pamr_scratch_bytes(int B, int K, int C, int H, int W, int D, int num_iter) {
+    (void)K;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return 0;
+    const size_t HW = (size_t)H * W;
+    const size_t wbytes = cl4::align_up(sizeof(float) * (size_t)B * 8 * D * HW, 256);
+    const size_t mbytes = (num_iter >= 2) ? cl4::align_up(sizeof(float) * (size_t)B * C * HW, 256) : 0;
+    return wbytes + mbytes;
+}
+
+extern "C" int cl4_pamr_forward(const float* img, const float* mask_in, float* mask_out, void* scratch,
+                                size_t scratch_bytes, int B, int K, int C, int H, int W, const int* dilations, int D,
+                                int num_iter, cl4_stream_t stream) {
+    using namespace cl4;
+    int rc = check_plane("pamr_forward", B, H, W);
+    if (rc != CL4_OK) return rc;
+    CL4_REQUIRE(K >= 1 && C >= 1 && num_iter >= 0, CL4_EINVAL, "pamr_forward: bad K/C/num_iter");
+    if (B == 0) return CL4_OK;
+    CL4_REQUIRE(img && mask_in && mask_out && mask_in != mask_out, CL4_EINVAL, "pamr_forward: null or aliased pointers");
+    const size_t HW = (size_t)H * W;
+    const size_t nmask = sizeof(float) * (size_t)B * C * HW;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (num_iter == 0) {
+        cudaError_t e = cudaMemcpyAsync(mask_out, mask_in, nmask, cudaMemcpyDeviceToDevice, s);
+        CL4_REQUIRE(e == cudaSuccess, CL4_ECUDA, "pamr_forward: copy: %s", cudaGetErrorString(e));
+        return CL4_OK;
+    }
+    CL4_REQUIRE(scratch && scratch_bytes >= cl4_pamr_scratch_bytes(B, K, C, H, W, D, num_iter), CL4_ESCRATCH,
+                "pamr_forward: scratch too small");
+    float* wts = reinterpret_cast<float*>(scratch);
+    float* tmp = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) +
+                                          align_up(sizeof(float) * (size_t)B * 8 * D * HW, 256));
+    rc = cl4_pamr_weights(img, wts, B, K, H, W, dilations, D, stream);
+    if (rc != CL4_OK) return rc;
+    // ping-pong so that the last sweep lands in mask_out: in -> (tmp|out) -> ... -> out
+    const float* cur = mask_in;
+    for (int it = 0; it < num_iter; ++it) {
+        const int remaining = num_iter - it;  // sweeps left including this one
+        float* dst = (remaining & 1) ? mask_out : tmp;
+        rc = cl4_pamr_sweep(wts, cur, dst, B, C, H, W, dilations, D, stream);
+        if (rc != CL4_OK) return rc;
+        cur = dst;
+    }
+    return CL4_OK;
+}

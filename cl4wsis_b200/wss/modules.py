@@ -1,0 +1,117 @@
+"""Drop-in ``PAMR`` (reference wss/modules.py:122-152) on hand-written sm_100a kernels.
+
+The module keeps the reference's constructor, attribute and buffer names
+(``aff_x``, ``aff_m``, ``aff_std``, each with a ``kernel`` buffer and a
+``dilations`` attribute — wss/modules.py:19-45, :65-83, :86-102) so that
+``state_dict()`` of anything embedding it is unchanged, but the
+forward pass never touches those buffers: it calls ``cl4_pamr_forward``.
+"""
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+_TAPS8 = [(0, 0), (0, 1), (0, 2), (1, 0), (1, 2), (2, 0), (2, 1), (2, 2)]
+
+
+class _Stencil(nn.Module):
+    """Holds the 3x3 shift-stencil buffer of the reference helper modules (state only)."""
+
+    def __init__(self, dilations=[1]):
+        super().__init__()
+        self.dilations = dilations
+        self.register_buffer("kernel", self._init_aff())
+
+    def _init_aff(self):
+        raise NotImplementedError
+
+
+class LocalAffinity(_Stencil):
+    """centre minus neighbour (wss/modules.py:26-45)."""
+
+    def _init_aff(self):
+        k = torch.zeros(8, 1, 3, 3)
+        for i, (r, c) in enumerate(_TAPS8):
+            k[i, 0, 1, 1] = 1
+            k[i, 0, r, c] = -1
+        return k
+
+
+class LocalAffinityAbs(LocalAffinity):
+    """|centre - neighbour| (wss/modules.py:115-119)."""
+
+
+class LocalAffinityCopy(_Stencil):
+    """neighbour gather (wss/modules.py:65-83)."""
+
+    def _init_aff(self):
+        k = torch.zeros(8, 1, 3, 3)
+        for i, (r, c) in enumerate(_TAPS8):
+            k[i, 0, r, c] = 1
+        return k
+
+
+class LocalStDev(_Stencil):
+    """9-tap gather feeding the unbiased std (wss/modules.py:86-112)."""
+
+    def _init_aff(self):
+        k = torch.zeros(9, 1, 3, 3)
+        for i in range(9):
+            k[i, 0, i // 3, i % 3] = 1
+        return k
+
+
+class PAMR(nn.Module):
+    """``PAMR(num_iter=10, dilations=[1,2,4,8,12,24]).forward(x, mask)`` — wss/modules.py:122-152.
+
+    x: [B,K,H,W] fp32 image (denormalised RGB in the trainer, train.py:376-379);
+    mask: [B,C,h,w] fp32; returns the refined mask [B,C,H,W] fp32 on the same device.
+    """
+
+    def __init__(self, num_iter=10, dilations=[1, 2, 4, 8, 12, 24]):
+        super().__init__()
+        self.num_iter = num_iter
+        self.aff_x = LocalAffinityAbs(dilations)
+        self.aff_m = LocalAffinityCopy(dilations)
+        self.aff_std = LocalStDev(dilations)
+
+    @torch.no_grad()
+    def forward(self, x, mask):
+        return pamr_forward(x, mask, self.num_iter, self.aff_x.dilations)
+
+
+def _as_f32(t, name):
+    _lib.require_cuda(t, name)
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (got {t.dtype}); run PAMR outside autocast (SURVEY D4)")
+    return t.detach().contiguous()
+
+
+def pamr_forward(x, mask, num_iter, dilations):
+    lib = _lib.load()
+    x = _as_f32(x, "x")
+    mask = _as_f32(mask, "mask")
+    if x.dim() != 4 or mask.dim() != 4:
+        raise ValueError("PAMR expects x [B,K,H,W] and mask [B,C,h,w]")
+    if x.device != mask.device:
+        raise RuntimeError("x and mask must be on the same device")
+    B, K, H, W = x.shape
+    Bm, C, h, w = mask.shape
+    if Bm != B:
+        raise RuntimeError(f"batch mismatch between x ({B}) and mask ({Bm})")
+    dil = [int(d) for d in dilations]
+    with torch.cuda.device(x.device):
+        st = _lib.stream_ptr(x.device)
+        if (h, w) != (H, W):  # F.interpolate(..., bilinear, align_corners=True)  wss/modules.py:134
+            m_in = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+            _lib.check(lib.cl4_resize_bilinear_ac(_lib.ptr(mask), _lib.ptr(m_in), B * C, h, w, H, W, st), "resize")
+        else:
+            m_in = mask
+        out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+        if B == 0 or C == 0:
+            return out
+        nbytes = lib.cl4_pamr_scratch_bytes(B, K, C, H, W, len(dil), int(num_iter))
+        scratch = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=x.device)
+        _lib.check(lib.cl4_pamr_forward(_lib.ptr(x), _lib.ptr(m_in), _lib.ptr(out), _lib.ptr(scratch), nbytes,
+                                        B, K, C, H, W, _lib.int_array(dil), len(dil), int(num_iter), st), "PAMR")
+    return out

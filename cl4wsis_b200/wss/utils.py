@@ -1,0 +1,43 @@
+"""Drop-in ``peak_extract`` (reference wss/utils.py:3-25) on the sm_100a NMS + top-K kernels."""
+import torch
+
+from .. import _lib
+
+
+def peak_extract_device(heat, kernel=5, K=25):
+    """Device-resident variant: returns (scores f32, ys i32, xs i32) CUDA tensors [B,C,K]."""
+    lib = _lib.load()
+    _lib.require_cuda(heat, "heat")
+    if heat.dim() != 4:
+        raise ValueError("peak_extract expects heat [B,C,H,W]")
+    heat = heat.detach()
+    if heat.dtype != torch.float32:
+        heat = heat.float()
+    heat = heat.contiguous()
+    B, C, H, W = heat.shape
+    if kernel % 2 == 0:
+        # the reference fails at `hmax == heat` (wss/utils.py:11): an even kernel shrinks the pooled map
+        raise RuntimeError(f"peak_extract: even kernel {kernel} makes max_pool2d's output smaller than heat")
+    if K > H * W:
+        raise RuntimeError("selected index k out of range")  # torch.topk's message
+    dev = heat.device
+    with torch.cuda.device(dev):
+        scores = torch.empty((B, C, K), dtype=torch.float32, device=dev)
+        ys = torch.empty((B, C, K), dtype=torch.int32, device=dev)
+        xs = torch.empty((B, C, K), dtype=torch.int32, device=dev)
+        if B * C == 0:
+            return scores, ys, xs
+        nbytes = lib.cl4_peak_extract_scratch_bytes(B, C, H, W, int(kernel), int(K))
+        scratch = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        _lib.check(lib.cl4_peak_extract(_lib.ptr(heat), _lib.ptr(scores), _lib.ptr(ys), _lib.ptr(xs),
+                                        _lib.ptr(scratch), nbytes, B, C, H, W, int(kernel), int(K),
+                                        _lib.stream_ptr(dev)), "peak_extract")
+    return scores, ys, xs
+
+
+def peak_extract(heat, kernel=5, K=25):
+    """Reference signature and return types: three numpy arrays [B,C,K] (f32, i32, i32),
+    sorted by score; ties broken by the lower flat index (the reference leaves tie order
+    to torch.topk)."""
+    scores, ys, xs = peak_extract_device(heat, kernel, K)
+    return scores.cpu().numpy(), ys.cpu().numpy(), xs.cpu().numpy()

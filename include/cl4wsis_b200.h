@@ -1,0 +1,120 @@
+/*
+ * cl4wsis_b200.h — C ABI of the B200-native (sm_100a) pseudo-label hot path of CL4WSIS.
+ *
+ * This is the drop-in boundary.  The reference has no native code and therefore
+ * no FFI of its own ("zero native code"); each entry point below
+ * replaces the body of one reference Python function, cited per function
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes
+ * binding a reference maintainer would add.
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; every tensor is contiguous NCHW fp32 unless
+ *     stated otherwise; all data pointers are DEVICE pointers on the current
+ *     CUDA device; the caller owns every buffer, including scratch;
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and
+ *     returns immediately; nothing here synchronises or allocates;
+ *   - return value: CL4_OK (0) or a negative error code; never throws;
+ *     cl4_last_error() gives a thread-local message for the last failure.
+ */
+#ifndef CL4WSIS_B200_H_
+#define CL4WSIS_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CL4_OK 0
+#define CL4_EINVAL (-1)       /* bad shape / null pointer / bad parameter            */
+#define CL4_EUNSUPPORTED (-2) /* valid in the reference but outside this build's range */
+#define CL4_ECUDA (-3)        /* a CUDA runtime call or launch failed                  */
+#define CL4_ESCRATCH (-4)     /* scratch buffer too small                              */
+
+#define CL4_MAX_DILATIONS 8
+#define CL4_MAX_TOPK 256
+
+typedef void* cl4_stream_t; /* cudaStream_t */
+
+/* ABI version (bumped on any signature change) and last error text. */
+int cl4_abi_version(void);
+const char* cl4_last_error(void);
+
+/* ------------------------------------------------------------------------- *
+ * PAMR — wss/modules.py:122-152 (class PAMR), stencils :17-119.
+ * ------------------------------------------------------------------------- */
+
+/* F.interpolate(mask, size=(H,W), mode="bilinear", align_corners=True), the first
+ * line of PAMR.forward (wss/modules.py:134).  in [planes,h,w] -> out [planes,H,W]. */
+int cl4_resize_bilinear_ac(const float* in, float* out, int planes, int h, int w, int H, int W,
+                           cl4_stream_t stream);
+
+/* Affinity weights, wss/modules.py:141-145:
+ *   w = softmax_p( mean_k( -|x_k - shift_p x_k| / (1e-8 + 0.1 * std_k) ) )
+ * img [B,K,H,W] -> w [B,8*D,H,W] (p = dilation_index*8 + tap, taps in the
+ * LocalAffinity order wss/modules.py:30-40; replicate padding :57). */
+int cl4_pamr_weights(const float* img, float* w, int B, int K, int H, int W, const int* dilations, int D,
+                     cl4_stream_t stream);
+
+/* One propagation sweep, wss/modules.py:148-149:
+ *   mask_out[b,c] = sum_p w[b,p] * shift_p(mask_in[b,c])
+ * mask_in must not alias mask_out. */
+int cl4_pamr_sweep(const float* w, const float* mask_in, float* mask_out, int B, int C, int H, int W,
+                   const int* dilations, int D, cl4_stream_t stream);
+
+/* Whole PAMR.forward after the resize: weights + num_iter sweeps.
+ * img [B,K,H,W], mask_in [B,C,H,W] -> mask_out [B,C,H,W].  scratch must hold
+ * cl4_pamr_scratch_bytes(...) bytes (weights + one ping-pong mask buffer).
+ * mask_in is not modified; mask_out may not alias mask_in. */
+size_t cl4_pamr_scratch_bytes(int B, int K, int C, int H, int W, int D, int num_iter);
+int cl4_pamr_forward(const float* img, const float* mask_in, float* mask_out, void* scratch,
+                     size_t scratch_bytes, int B, int K, int C, int H, int W, const int* dilations, int D,
+                     int num_iter, cl4_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * peak_extract — wss/utils.py:3-25.
+ *   keep = (max_pool2d(heat,k,1,(k-1)//2) == heat); peak = heat*keep;
+ *   top-K of peak per (b,c) plane, sorted by (score desc, flat index asc);
+ *   ys = int(float(idx)/W), xs = idx % W.
+ * heat [B,C,H,W] -> scores f32 [B,C,K], ys i32 [B,C,K], xs i32 [B,C,K] (device).
+ * kernel must be odd (an even kernel raises in the reference: shape mismatch at
+ * wss/utils.py:11); 1 <= K <= min(H*W, CL4_MAX_TOPK).
+ * ------------------------------------------------------------------------- */
+size_t cl4_peak_extract_scratch_bytes(int B, int C, int H, int W, int kernel, int K);
+int cl4_peak_extract(const float* heat, float* scores, int* ys, int* xs, void* scratch, size_t scratch_bytes,
+                     int B, int C, int H, int W, int kernel, int K, cl4_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * find_instance_center — modules/utils.py:463-502 (twin: dataset/utils.py:623-661),
+ * batched over N independent [H,W] heat-maps.
+ *   t = x > thr ? x : -1; p = max_pool2d(t,k,1,(k-1)//2); centre iff t == p and t > min_value
+ *   (min_value = 0 reproduces :492; the reference's degenerate top_k branch
+ *   :500-502 re-runs the same test with another min_value).
+ * ctr_out [N,max_out,2] int64 (y,x) in torch.nonzero (row-major) order;
+ * count_out [N] int32 = TOTAL number of centres per map (may exceed max_out; only
+ * the first max_out are written).  heat is not modified.
+ * ------------------------------------------------------------------------- */
+size_t cl4_center_nms_scratch_bytes(int N, int H, int W);
+int cl4_center_nms(const float* heat, float threshold, float min_value, int kernel, int N, int H, int W,
+                   long long* ctr_out, int* count_out, int max_out, void* scratch, size_t scratch_bytes,
+                   cl4_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * group_pixels — modules/utils.py:505-542, with the `(fg * ins_seg).long()` of
+ * get_instance_segmentation (:606) folded in when fg != NULL; batched over N.
+ *   id = 1 + argmin_k sqrt_rn(fma_rn(dx,dx,rn(dy*dy))), first minimum wins,
+ *   dy = float(ctr_y) - (float(y) + off_y), dx likewise.
+ * ctr [N,ctr_stride,2] int64 (y,x); the number of centres of map n is
+ * count_dev[n] (device int32, clamped to ctr_stride) when count_dev != NULL,
+ * else Kc for every map.  offsets [N,2,H,W]; fg [N,H,W] uint8 (0/1) or NULL;
+ * ids [N,H,W] int64.  A map with zero centres gets all-zero ids when
+ * empty_mode == 0 (ignore=True, :597-598) or fg (as 0/1) when empty_mode == 1 (:599-600).
+ * ------------------------------------------------------------------------- */
+int cl4_group_pixels(const long long* ctr, const int* count_dev, int Kc, int ctr_stride, const float* offsets,
+                     const unsigned char* fg, long long* ids, int N, int H, int W, int empty_mode,
+                     cl4_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CL4WSIS_B200_H_ */

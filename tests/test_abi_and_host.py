@@ -1,0 +1,99 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol the header
+declares (no compute calls), the ctypes table matches the header, and host-side argument
+validation mirrors the reference's error behaviour without touching a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "cl4wsis_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(cl4_[a-z0-9_]+)\s*\(", hdr)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from cl4wsis_b200 import build
+    build.build()
+    from cl4wsis_b200 import _lib
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = _declared_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/cl4wsis_b200.h but not exported"
+
+
+def test_ctypes_table_matches_header():
+    from cl4wsis_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared_symbols()
+
+
+def test_abi_version_and_scratch_queries(lib):
+    assert lib.cl4_abi_version() == 1
+    # pure host arithmetic, no CUDA call: weights [B,48,H,W] + one ping-pong mask buffer
+    n = lib.cl4_pamr_scratch_bytes(16, 3, 21, 512, 512, 6, 10)
+    assert n == 4 * 16 * 512 * 512 * (48 + 21)
+    assert lib.cl4_pamr_scratch_bytes(16, 3, 21, 512, 512, 6, 1) == 4 * 16 * 512 * 512 * 48
+    assert lib.cl4_center_nms_scratch_bytes(1, 512, 512) >= 512 * 16 * 4 + 512 * 4
+    assert lib.cl4_peak_extract_scratch_bytes(2, 3, 64, 64, 15, 25) == 2 * 3 * 2 * 25 * 8
+
+
+def test_argument_validation_returns_codes_without_a_gpu(lib):
+    from cl4wsis_b200 import _lib
+    null = ctypes.c_void_p(0)
+    dil = _lib.int_array([1, 2])
+    assert lib.cl4_pamr_sweep(null, null, null, 1, 0, 8, 8, dil, 2, null) == _lib.CL4_EINVAL
+    assert lib.cl4_pamr_weights(null, null, 1, 3, 8, 8, dil, 9, null) == _lib.CL4_EUNSUPPORTED
+    assert b"dilations" in lib.cl4_last_error()
+    assert lib.cl4_pamr_weights(null, null, 1, 3, 8, 8, _lib.int_array([1, 0]), 2, null) == _lib.CL4_EINVAL
+    assert lib.cl4_center_nms(null, 0.1, 0.0, 4, 1, 8, 8, null, null, 0, null, 0, null) == _lib.CL4_EINVAL
+    assert b"odd" in lib.cl4_last_error()
+    assert lib.cl4_peak_extract(null, null, null, null, null, 0, 1, 1, 8, 8, 3, 65, null) == _lib.CL4_EINVAL
+    assert lib.cl4_peak_extract(null, null, null, null, null, 0, 1, 1, 64, 64, 3, 300, null) == _lib.CL4_EUNSUPPORTED
+    assert lib.cl4_group_pixels(null, null, 1, 1, null, null, null, 1, 8, 8, 0, null) == _lib.CL4_EINVAL
+    with pytest.raises(ValueError):
+        _lib.check(_lib.CL4_EINVAL, "x")
+    with pytest.raises(NotImplementedError):
+        _lib.check(_lib.CL4_EUNSUPPORTED, "x")
+
+
+def test_no_cpu_fallback_and_reference_error_conventions():
+    import cl4wsis_b200 as cl4
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cl4.PAMR()(torch.rand(1, 3, 8, 8), torch.rand(1, 2, 8, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cl4.peak_extract(torch.rand(1, 1, 8, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cl4.find_instance_center(torch.rand(1, 1, 8, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cl4.group_pixels(torch.zeros(1, 2, dtype=torch.long), torch.rand(1, 2, 8, 8))
+
+
+def test_pamr_module_mirrors_reference_state():
+    import cl4wsis_b200 as cl4
+    mod = cl4.PAMR(num_iter=10, dilations=[1, 2, 4, 8, 12])
+    assert mod.num_iter == 10 and mod.aff_x.dilations == [1, 2, 4, 8, 12]
+    sd = mod.state_dict()
+    assert sorted(sd) == ["aff_m.kernel", "aff_std.kernel", "aff_x.kernel"]
+    k = sd["aff_x.kernel"]
+    assert float(k[0, 0, 1, 1]) == 1 and float(k[0, 0, 0, 0]) == -1 and float(k[4, 0, 1, 2]) == -1
+    assert float(sd["aff_m.kernel"].sum()) == 8 and float(sd["aff_std.kernel"].sum()) == 9
+    assert len(list(mod.parameters())) == 0
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cl4wsis_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(d, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "cl4_oracle" not in src, f

@@ -1,0 +1,286 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the drop-in Python mirrors)
+against the CPU oracle and the reference-generated golden fixtures.
+
+Bars: refined masks allclose(rtol=1e-4, atol=1e-6) in fp32; centre lists,
+peak indices and instance-id maps bit-exact.
+"""
+import io
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-4, 1e-6
+PAMR_CASES = ["pamr_d6", "pamr_d5", "pamr_tiny_d6", "pamr_1iter", "pamr_flat", "pamr_resize", "pamr_c21_64"]
+
+
+@pytest.fixture(scope="module")
+def cl4():
+    import cl4wsis_b200
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    cl4wsis_b200._lib.load()
+    return cl4wsis_b200
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# --------------------------------------------------------------------------- PAMR
+@pytest.mark.parametrize("name", PAMR_CASES)
+def test_pamr_golden(cl4, golden, name):
+    x, m, ref = golden[name + "__x"], golden[name + "__mask"], golden[name + "__out"]
+    mod = cl4.PAMR(num_iter=int(golden[name + "__T"]), dilations=golden[name + "__dil"].tolist()).cuda()
+    got = mod(cuda(x), cuda(m)).cpu().numpy()
+    assert got.shape == ref.shape and got.dtype == np.float32
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("B,C,H,W,dil,T", [
+    (2, 21, 96, 80, [1, 2, 4, 8, 12, 24], 10),
+    (1, 7, 33, 65, [1, 2, 4, 8, 12], 10),
+    (3, 2, 17, 130, [1, 2, 4, 8, 12, 24], 4),
+    (1, 1, 5, 3, [1, 2, 4, 8, 12, 24], 10),      # every dilation exceeds the image
+    (2, 3, 32, 32, [1, 2, 4, 8, 12], 10),        # the trainer's feature-resolution regime
+    (1, 81, 56, 56, [1, 2, 4, 8, 12], 10),       # coco-voc feature resolution, 81 classes
+    (1, 4, 40, 40, [3], 2),
+    (1, 4, 40, 40, [1, 2, 3, 4, 5, 6, 7, 8], 2),
+    (1, 3, 24, 24, [1, 2, 4], 0),                # num_iter = 0 returns the (resized) mask
+])
+def test_pamr_oracle_random(cl4, oracle, B, C, H, W, dil, T):
+    rng = np.random.default_rng(B * 1000 + C * 100 + H + W)
+    x = (rng.integers(0, 256, (B, 3, H, W)) / 255.0).astype(np.float32)
+    m = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).softmax(1).numpy()
+    want = oracle.pamr(x, m, T, dil)
+    got = cl4.PAMR(T, dil).cuda()(cuda(x), cuda(m)).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
+
+
+def test_pamr_weights_and_single_sweep(cl4, oracle, golden):
+    """The two kernels separately, through the C ABI."""
+    lib, L = cl4._lib.load(), cl4._lib
+    x = golden["weights_d6__x"]
+    dil = [1, 2, 4, 8, 12, 24]
+    B, K, H, W = x.shape
+    xd = cuda(x)
+    w = torch.empty((B, 48, H, W), dtype=torch.float32, device="cuda")
+    L.check(lib.cl4_pamr_weights(L.ptr(xd), L.ptr(w), B, K, H, W, L.int_array(dil), 6, L.stream_ptr()), "weights")
+    np.testing.assert_allclose(w.cpu().numpy(), golden["weights_d6__w"], rtol=1e-4, atol=1e-7)
+    m = np.random.default_rng(3).random((B, 5, H, W)).astype(np.float32)
+    md, out = cuda(m), torch.empty((B, 5, H, W), dtype=torch.float32, device="cuda")
+    L.check(lib.cl4_pamr_sweep(L.ptr(w), L.ptr(md), L.ptr(out), B, 5, H, W, L.int_array(dil), 6, L.stream_ptr()), "sweep")
+    # one sweep == PAMR with num_iter=1
+    np.testing.assert_allclose(out.cpu().numpy(), oracle.pamr(x, m, 1, dil), rtol=RTOL, atol=ATOL)
+
+
+def test_pamr_module_state_and_errors(cl4):
+    mod = cl4.PAMR(num_iter=10, dilations=[1, 2, 4, 8, 12])
+    sd = mod.state_dict()
+    assert sorted(sd) == ["aff_m.kernel", "aff_std.kernel", "aff_x.kernel"]
+    assert tuple(sd["aff_x.kernel"].shape) == (8, 1, 3, 3) and tuple(sd["aff_std.kernel"].shape) == (9, 1, 3, 3)
+    assert len(list(mod.parameters())) == 0
+    with pytest.raises(RuntimeError):
+        mod(torch.rand(1, 3, 8, 8), torch.rand(1, 2, 8, 8))  # CPU tensors: no fallback
+    with pytest.raises(TypeError):
+        mod.cuda()(torch.rand(1, 3, 8, 8, device="cuda").half(), torch.rand(1, 2, 8, 8, device="cuda"))
+    with pytest.raises(NotImplementedError):
+        cl4.PAMR(1, list(range(1, 10))).cuda()(torch.rand(1, 3, 8, 8, device="cuda"), torch.rand(1, 2, 8, 8, device="cuda"))
+
+
+def test_pamr_full_size_properties(cl4):
+    """BASELINE config 2 shape (B cut to 2): channel sums stay 1 (SURVEY §8c ③), linearity in
+    the mask, and a constant mask is a fixed point (weights sum to 1)."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B, C, H, W = 2, 21, 512, 512
+    x = (torch.randint(0, 256, (B, 3, H, W), generator=g).float() / 255).cuda()
+    m1 = torch.randn((B, C, H, W), generator=g).softmax(1).cuda()
+    m2 = torch.rand((B, C, H, W), generator=g).cuda()
+    mod = cl4.PAMR(10, [1, 2, 4, 8, 12, 24]).cuda()
+    o1, o2 = mod(x, m1), mod(x, m2)
+    assert torch.allclose(o1.sum(1), torch.ones_like(o1[:, 0]), rtol=0, atol=2e-5)
+    o12 = mod(x, 0.25 * m1 + 0.75 * m2)
+    assert torch.allclose(o12, 0.25 * o1 + 0.75 * o2, rtol=1e-4, atol=1e-6)
+    const = torch.full((B, C, H, W), 0.37, device="cuda")
+    assert torch.allclose(mod(x, const), const, rtol=0, atol=2e-6)
+    assert float(o1.min()) >= 0.0 and float(o1.max()) <= 1.0 + 1e-5
+
+
+def test_pamr_full_size_tile_vs_oracle(cl4, oracle):
+    """One 512x512 image, 3 classes, against the oracle (finishes in seconds on CPU)."""
+    rng = np.random.default_rng(77)
+    x = (rng.integers(0, 256, (1, 3, 512, 512)) / 255.0).astype(np.float32)
+    m = torch.from_numpy(rng.standard_normal((1, 3, 512, 512)).astype(np.float32)).softmax(1).numpy()
+    want = oracle.pamr(x, m, 10, [1, 2, 4, 8, 12, 24])
+    got = cl4.PAMR().cuda()(cuda(x), cuda(m)).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
+
+
+# --------------------------------------------------------------------------- peak_extract
+def _check_peaks(got, want, heat):
+    sc, ys, xs = got
+    ws, wy, wx = want
+    assert sc.dtype == np.float32 and ys.dtype == np.int32 and xs.dtype == np.int32
+    assert np.array_equal(sc, ws)
+    # same tie rule as the oracle (score desc, flat index asc): indices are exact everywhere
+    assert np.array_equal(ys, wy) and np.array_equal(xs, wx)
+
+
+@pytest.mark.parametrize("name", ["peak_k15", "peak_k5", "peak_k3_neg", "peak_kat8"])
+def test_peak_extract_golden(cl4, oracle, golden, name):
+    heat = golden[name + "__heat"]
+    k, K = int(golden[name + "__kernel"]), int(golden[name + "__K"])
+    got = cl4.peak_extract(cuda(heat), kernel=k, K=K)
+    _check_peaks(got, oracle.peak_extract(heat, k, K), heat)
+    # against the reference itself: scores exact; indices where the score is positive and unique
+    rs, ry, rx = golden[name + "__scores"], golden[name + "__ys"], golden[name + "__xs"]
+    assert np.array_equal(got[0], rs)
+    for b in range(rs.shape[0]):
+        for c in range(rs.shape[1]):
+            s = rs[b, c]
+            uniq = np.array([(s == v).sum() == 1 for v in s]) & (s != 0)
+            assert np.array_equal(got[1][b, c][uniq], ry[b, c][uniq])
+            assert np.array_equal(got[2][b, c][uniq], rx[b, c][uniq])
+
+
+@pytest.mark.parametrize("B,C,H,W,kernel,K", [(2, 20, 128, 96, 15, 25), (1, 3, 70, 33, 5, 40), (1, 2, 64, 64, 41, 100),
+                                              (1, 1, 9, 9, 3, 81), (1, 2, 200, 300, 15, 256)])
+def test_peak_extract_oracle_random(cl4, oracle, B, C, H, W, kernel, K):
+    rng = np.random.default_rng(H * W + K)
+    heat = rng.random((B, C, H, W)).astype(np.float32)
+    heat[:, :, : H // 2] = np.round(heat[:, :, : H // 2] * 16) / 16  # exact ties and plateaus
+    heat[:, 0, H // 2:, : W // 2] = 0.0                              # zero fillers
+    _check_peaks(cl4.peak_extract(cuda(heat), kernel=kernel, K=K), oracle.peak_extract(heat, kernel, K), heat)
+
+
+def test_peak_extract_errors(cl4):
+    h = torch.rand(1, 1, 8, 8, device="cuda")
+    with pytest.raises(RuntimeError):
+        cl4.peak_extract(h, kernel=4, K=3)
+    with pytest.raises(RuntimeError):
+        cl4.peak_extract(h, kernel=3, K=65)
+    with pytest.raises(NotImplementedError):
+        cl4.peak_extract(torch.rand(1, 1, 32, 32, device="cuda"), kernel=3, K=300)
+    with pytest.raises(RuntimeError):
+        cl4.peak_extract(torch.rand(1, 1, 8, 8), kernel=3, K=3)
+
+
+# --------------------------------------------------------------------------- find_instance_center
+def test_find_instance_center_golden(cl4, golden):
+    for i in range(int(golden["center__n"])):
+        thr, k, topk = golden[f"center_{i}__args"]
+        topk = None if topk < 0 else int(topk)
+        heat = cuda(golden[f"center_{i}__heat"])
+        before = heat.clone()
+        with redirect_stdout(io.StringIO()) as so:
+            got = cl4.find_instance_center(heat, float(thr), int(k), topk)
+        ref = golden[f"center_{i}__ctr"]
+        assert got.dtype == torch.int64 and got.is_cuda and tuple(got.shape) == ref.shape, i
+        assert np.array_equal(got.cpu().numpy(), ref), i
+        assert torch.equal(heat, before)  # input not modified
+        if f"center_{i}__printed" in golden.files:
+            assert int(so.getvalue().strip()) == int(golden[f"center_{i}__printed"])  # SURVEY §8c ⑦
+
+
+@pytest.mark.parametrize("H,W,k,thr", [(512, 512, 41, 0.3), (100, 333, 3, 0.1), (65, 31, 7, 0.5), (33, 1, 5, 0.2),
+                                       (1, 200, 9, 0.2), (256, 256, 1, 0.6)])
+def test_find_instance_center_oracle_random(cl4, oracle, H, W, k, thr):
+    rng = np.random.default_rng(H + 7 * W + k)
+    heat = rng.random((1, 1, H, W)).astype(np.float32)
+    heat = np.round(heat * 32) / 32  # ties
+    heat[0, 0, : H // 3] = np.nan if H > 64 else heat[0, 0, : H // 3]  # NaN rows suppress their windows
+    want = oracle.find_instance_center(heat, thr, k)
+    got = cl4.find_instance_center(cuda(heat), thr, k).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+def test_find_instance_center_many_centres(cl4, oracle):
+    # more centres than the wrapper's first capacity guess (4096)
+    heat = np.zeros((1, 1, 256, 256), np.float32)
+    heat[0, 0, ::2, ::2] = 0.5
+    got = cl4.find_instance_center(cuda(heat), 0.3, 1).cpu().numpy()
+    assert got.shape == (128 * 128, 2) and np.array_equal(got, oracle.find_instance_center(heat, 0.3, 1))
+
+
+def test_find_instance_center_errors(cl4):
+    with pytest.raises(ValueError, match="batch size = 1"):
+        cl4.find_instance_center(torch.zeros(2, 1, 8, 8, device="cuda"))
+    with pytest.raises(AssertionError):
+        cl4.find_instance_center(torch.zeros(1, 2, 8, 8, device="cuda"))
+    with pytest.raises(RuntimeError):
+        cl4.find_instance_center(torch.zeros(1, 1, 8, 8, device="cuda"), 0.1, 4)
+
+
+# --------------------------------------------------------------------------- group_pixels
+def test_group_pixels_golden(cl4, golden):
+    for i in range(int(golden["group__n"])):
+        got = cl4.group_pixels(cuda(golden[f"group_{i}__ctr"]), cuda(golden[f"group_{i}__off"]))
+        ref = golden[f"group_{i}__ids"]
+        assert got.dtype == torch.int64 and tuple(got.shape) == ref.shape
+        assert np.array_equal(got.cpu().numpy(), ref), i
+
+
+@pytest.mark.parametrize("H,W,Kc", [(512, 512, 5), (1024, 1024, 200), (33, 31, 7), (17, 19, 1), (64, 50, 3000), (5, 3, 2)])
+def test_group_pixels_oracle_random(cl4, oracle, H, W, Kc):
+    rng = np.random.default_rng(H * 3 + W + Kc)
+    ctr = np.stack([rng.integers(0, H, Kc), rng.integers(0, W, Kc)], 1).astype(np.int64)
+    off = (rng.standard_normal((1, 2, H, W)) * 15).astype(np.float32)
+    off[0, :, : H // 4] = np.round(off[0, :, : H // 4])  # integer offsets: exact distance ties
+    want = oracle.group_pixels(ctr, off)
+    got = cl4.group_pixels(cuda(ctr), cuda(off)).cpu().numpy()
+    assert np.array_equal(got, want), int((got != want).sum())
+    assert got.min() >= 1 and got.max() <= Kc
+
+
+def test_group_pixels_errors(cl4):
+    with pytest.raises(ValueError, match="batch size = 1"):
+        cl4.group_pixels(torch.zeros(1, 2, dtype=torch.long, device="cuda"), torch.zeros(2, 2, 8, 8, device="cuda"))
+    with pytest.raises(RuntimeError):
+        cl4.group_pixels(torch.zeros(1, 2, dtype=torch.long), torch.zeros(1, 2, 8, 8))
+
+
+# --------------------------------------------------------------------------- get_instance_segmentation
+def test_get_instance_segmentation_golden_beta0(cl4, golden):
+    seen = 0
+    for i in range(int(golden["inst__n"])):
+        thr, k, ignore, beta = golden[f"inst_{i}__args"]
+        if beta > 0:
+            continue
+        hm = cuda(golden[f"inst_{i}__heat"])
+        got = cl4.get_instance_segmentation(cuda(golden[f"inst_{i}__fg"]), hm, cuda(golden[f"inst_{i}__off"]),
+                                            threshold=float(thr), nms_kernel=int(k), top_k=None, ignore=bool(ignore),
+                                            beta=0)
+        assert got.dtype == torch.int64
+        assert np.array_equal(got.cpu().numpy(), golden[f"inst_{i}__ids"]), i
+        seen += 1
+    assert seen >= 3
+
+
+# --------------------------------------------------------------------------- batched step
+def test_pseudo_label_step_matches_per_image_oracle(cl4, oracle):
+    rng = np.random.default_rng(2024)
+    B, C, H, W = 3, 4, 96, 128
+    x = (rng.integers(0, 256, (B, 3, H, W)) / 255.0).astype(np.float32)
+    m = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).softmax(1).numpy()
+    heat = np.zeros((B, 1, H, W), np.float32)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    for b in range(B):
+        for _ in range(b * 3):  # image 0 has no centre at all
+            cy, cx, a = rng.integers(0, H), rng.integers(0, W), rng.uniform(0.4, 1.0)
+            heat[b, 0] = np.maximum(heat[b, 0], a * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / 72.0))
+    off = (rng.standard_normal((B, 2, H, W)) * 10).astype(np.float32)
+    step = cl4.PseudoLabelStep(B, C, H, W, num_iter=10, dilations=[1, 2, 4, 8, 12, 24], threshold=0.3, nms_kernel=41,
+                               max_centers=64)
+    refined, ids, counts, centers = step.run(cuda(x), cuda(m), cuda(heat), cuda(off))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(refined.cpu().numpy(), oracle.pamr(x, m, 10, [1, 2, 4, 8, 12, 24]), rtol=RTOL, atol=ATOL)
+    for b in range(B):
+        ctr = oracle.find_instance_center(heat[b:b + 1], 0.3, 41)
+        assert int(counts[b]) == ctr.shape[0]
+        assert np.array_equal(centers[b, : ctr.shape[0]].cpu().numpy(), ctr)
+        if ctr.shape[0] == 0:
+            assert int(ids[b].abs().sum()) == 0  # ignore=True: zeros (modules/utils.py:597-598)
+        else:
+            assert np.array_equal(ids[b].cpu().numpy(), oracle.group_pixels(ctr, off[b:b + 1])[0])
