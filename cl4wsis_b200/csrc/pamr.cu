@@ -8,7 +8,11 @@
 //
 // Data layout in HBM: image [B,K,H,W], weights [B,P,H,W] (planar per tap so that a warp's
 // read of one tap is one coalesced row segment), masks [B,C,H,W]; all fp32.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
+#include "pamr_internal.cuh"
 
 namespace cl4 {
 
@@ -234,6 +238,11 @@ extern "C" int cl4_pamr_sweep(const float* w, const float* mask_in, float* mask_
     if (rc != CL4_OK) return rc;
     if (B == 0) return CL4_OK;
     CL4_REQUIRE(w && mask_in && mask_out && mask_in != mask_out, CL4_EINVAL, "pamr_sweep: null or aliased pointers");
+    // CL4_SWEEP=v1 forces the register/L1 kernel (used by tests and A/B timing)
+    const char* force = getenv("CL4_SWEEP");
+    const bool want_tma = !(force && strcmp(force, "v1") == 0);
+    if (want_tma && D <= 6 && sweep_tma_applicable(C, H, W, dil, D, mask_in))
+        return launch_sweep_tma(w, mask_in, mask_out, B, C, H, W, dil, D, (cudaStream_t)stream);
     return dispatch_D<SweepLauncher>(D, w, mask_in, mask_out, B, C, H, W, dil, (cudaStream_t)stream);
 }
 
