@@ -17,10 +17,12 @@ namespace cl4 {
 constexpr int kTile = 32;
 constexpr int kHalo = 24;                       // largest supported dilation on this path
 constexpr int kBox = kTile + 2 * kHalo;         // 80
-constexpr int kStages = 3;
-constexpr int kSweepThreads = 512;              // 16 warps; thread (ty,tx) owns pixels (ty,tx) and (ty+16,tx)
+constexpr int kStages = 4;
+constexpr int kSweepThreads = 512;              // 16 warps; each thread owns two pixels 8 rows apart
+constexpr int kRowGap = 8;                      // (y, y+8): the d=8 and d=4 taps of the pair share 7 sources
 constexpr int kStageBytes = kBox * kBox * 4;    // 25600
-constexpr size_t kSweepSmem = (size_t)kStages * kStageBytes + 64;
+constexpr int kMaxFix = kBox * kBox - 1;        // out-of-image cells of a window (always < box area)
+constexpr size_t kSweepSmem = (size_t)kStages * kStageBytes + (size_t)kMaxFix * 4 + 128;
 
 // compile-time dilation sets get immediate LDS offsets; RuntimeDil keeps them in registers
 struct DilVoc6 {  // PAMR's class default (wss/modules.py:125)
@@ -40,6 +42,19 @@ struct DilRuntime {
     __host__ __device__ static constexpr int get(int) { return 1; }
 };
 
+struct TileCoord {
+    int b, y0, x0;
+};
+__device__ __forceinline__ TileCoord tile_coord(int t, int tiles_x, int tiles_per_img) {
+    TileCoord tc;
+    tc.b = t / tiles_per_img;
+    const int r = t - tc.b * tiles_per_img;
+    const int tyi = r / tiles_x;
+    tc.y0 = tyi * kTile;
+    tc.x0 = (r - tyi * tiles_x) * kTile;
+    return tc;
+}
+
 template <int D, class DS>
 __global__ void __launch_bounds__(kSweepThreads, 1)
 pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wts,
@@ -48,10 +63,15 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
     constexpr int P = 8 * D;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage0 = reinterpret_cast<float*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageBytes);
+    uint32_t* fixlist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kStages * kStageBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageBytes + (size_t)kMaxFix * 4 + 4);
+    uint64_t* empty = full + kStages;
+    __shared__ int s_nfix;
 
     const int tid = threadIdx.x;
-    const int tx = tid & 31, ty = tid >> 5;
+    const int lane = tid & 31, wrp = tid >> 5;
+    const int tx = lane;
+    const int ty = (wrp >> 3) * 16 + (wrp & 7);  // rows ty and ty + kRowGap
     const size_t HW = (size_t)H * W;
     const int tiles_per_img = tiles_x * tiles_y;
 
@@ -62,86 +82,113 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
     if (tid == 0) {
         tma_prefetch_desc(&tmap);
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kSweepThreads / 32);
+        }
         fence_mbar_init();
     }
     __syncthreads();
 
-    auto issue = [&](int item) {  // thread 0 only
-        const int k = item / C, c = item - k * C;
-        const int t = blockIdx.x + k * gridDim.x;
-        const int b = t / tiles_per_img, r = t - b * tiles_per_img;
-        const int tyi = r / tiles_x, txi = r - tyi * tiles_x;
-        const int s = item % kStages;
+    // ---- producer (thread 0 only): p_item is the next (tile, class) item to issue
+    int p_item = 0;
+    auto issue_next = [&]() {
+        const int pk = p_item / C, pc = p_item - pk * C;
+        const TileCoord ptc = tile_coord(blockIdx.x + pk * gridDim.x, tiles_x, tiles_per_img);
+        const int s = p_item % kStages;
+        if (p_item >= kStages) mbar_wait(&empty[s], (uint32_t)((p_item / kStages - 1) & 1));
         mbar_arrive_expect_tx(&full[s], kStageBytes);
-        tma_load_3d(stage0 + (size_t)s * (kBox * kBox), &tmap, &full[s], txi * kTile - kHalo, tyi * kTile - kHalo,
-                    b * C + c);
+        tma_load_3d(stage0 + (size_t)s * (kBox * kBox), &tmap, &full[s], ptc.x0 - kHalo, ptc.y0 - kHalo,
+                    ptc.b * C + pc);
+        ++p_item;
     };
     if (tid == 0) {
-        if (total > 0) issue(0);
-        if (total > 1) issue(1);
+        for (int i = 0; i < kStages - 1 && p_item < total; ++i) issue_next();
     }
 
     float w0[P], w1[P];
-    float* out0 = nullptr;
-    bool valid0 = false, valid1 = false, border = false;
-    int x0 = 0, y0 = 0;
     const int sbase = (ty + kHalo) * kBox + (tx + kHalo);
+    int item = 0;
 
-    for (int item = 0; item < total; ++item) {
-        const int k = item / C, c = item - k * C;
-        if (c == 0) {  // new tile: weights of this thread's two pixels
-            const int t = blockIdx.x + k * gridDim.x;
-            const int b = t / tiles_per_img, r = t - b * tiles_per_img;
-            const int tyi = r / tiles_x, txi = r - tyi * tiles_x;
-            x0 = txi * kTile;
-            y0 = tyi * kTile;
-            const int x = x0 + tx, ya = y0 + ty, yb = ya + 16;
-            valid0 = (x < W) && (ya < H);
-            valid1 = (x < W) && (yb < H);
-            border = (x0 < kHalo) || (y0 < kHalo) || (x0 + kTile + kHalo > W) || (y0 + kTile + kHalo > H);
-            const float* wp = wts + (size_t)b * P * HW + (size_t)ya * W + x;
+    for (int k = 0; k < n_my; ++k) {
+        const TileCoord tc = tile_coord(blockIdx.x + k * gridDim.x, tiles_x, tiles_per_img);
+        const int x = tc.x0 + tx, ya = tc.y0 + ty;
+        const bool valid0 = (x < W) && (ya < H);
+        const bool valid1 = (x < W) && (ya + kRowGap < H);
+        const bool border = (tc.x0 < kHalo) || (tc.y0 < kHalo) || (tc.x0 + kTile + kHalo > W) ||
+                            (tc.y0 + kTile + kHalo > H);
+        {  // weights of this thread's two pixels, kept in registers for all classes of the tile
+            const float* wp = wts + (size_t)tc.b * P * HW + (size_t)ya * W + x;
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 w0[p] = valid0 ? __ldg(wp + (size_t)p * HW) : 0.f;
-                w1[p] = valid1 ? __ldg(wp + (size_t)p * HW + (size_t)16 * W) : 0.f;
+                w1[p] = valid1 ? __ldg(wp + (size_t)p * HW + (size_t)kRowGap * W) : 0.f;
             }
-            out0 = mout + (size_t)b * C * HW + (size_t)ya * W + x;
         }
-        __syncthreads();  // every thread is done with item-1, whose stage is the one refilled next
-        if (tid == 0 && item + 2 < total) issue(item + 2);
-
-        const int s = item % kStages;
-        float* sm = stage0 + (size_t)s * (kBox * kBox);
-        mbar_wait(&full[s], (uint32_t)((item / kStages) & 1));
-
-        if (border) {  // replicate padding: out-of-image cells take the clamped in-image value
+        if (k + 1 < n_my) {  // pull the next tile's weights (P planes x 32 rows x 128 B) into L2
+            const TileCoord nt = tile_coord(blockIdx.x + (k + 1) * gridDim.x, tiles_x, tiles_per_img);
+            const float* nb = wts + (size_t)nt.b * P * HW + (size_t)nt.y0 * W + nt.x0;
+            for (int i = tid; i < P * kTile; i += kSweepThreads) {
+                const int p = i >> 5, r = i & 31;
+                if (nt.y0 + r < H) prefetch_l2(nb + (size_t)p * HW + (size_t)r * W);
+            }
+        }
+        int n_fix = 0;
+        if (border) {
+            // Replicate padding (wss/modules.py:57): list the window cells that fall outside the
+            // image together with the in-image cell they copy; the list is reused for every class.
+            if (tid == 0) s_nfix = 0;
+            __syncthreads();
             for (int i = tid; i < kBox * kBox; i += kSweepThreads) {
                 const int by = i / kBox, bx = i - by * kBox;
-                const int gy = y0 - kHalo + by, gx = x0 - kHalo + bx;
+                const int gy = tc.y0 - kHalo + by, gx = tc.x0 - kHalo + bx;
                 const int cy = clampi(gy, 0, H - 1), cx = clampi(gx, 0, W - 1);
-                if (cy != gy || cx != gx) sm[i] = sm[(cy - (y0 - kHalo)) * kBox + (cx - (x0 - kHalo))];
+                if (cy != gy || cx != gx) {
+                    const int src = (cy - (tc.y0 - kHalo)) * kBox + (cx - (tc.x0 - kHalo));
+                    fixlist[atomicAdd(&s_nfix, 1)] = ((uint32_t)i << 16) | (uint32_t)src;
+                }
             }
-            fence_proxy_async_smem();
             __syncthreads();
+            n_fix = s_nfix;
         }
+        float* out0 = mout + (size_t)tc.b * C * HW + (size_t)ya * W + x;
 
-        float a0 = 0.f, a1 = 0.f;
-        const float* sp = sm + sbase;
-#pragma unroll
-        for (int di = 0; di < D; ++di) {
-            const int d = DS::kStatic ? DS::get(di) : dil.d[di];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int dy = (j < 3) ? -1 : ((j < 5) ? 0 : 1);
-                const int dx = (j < 3) ? (j - 1) : ((j == 3) ? -1 : ((j == 4) ? 1 : (j - 6)));
-                const int off = dy * d * kBox + dx * d;
-                a0 = fmaf(w0[di * 8 + j], sp[off], a0);
-                a1 = fmaf(w1[di * 8 + j], sp[off + 16 * kBox], a1);
+        for (int c = 0; c < C; ++c, ++item) {
+            if (tid == 0 && p_item < total) issue_next();  // refills the stage released by item-1
+
+            const int s = item % kStages;
+            float* sm = stage0 + (size_t)s * (kBox * kBox);
+            mbar_wait(&full[s], (uint32_t)((item / kStages) & 1));
+
+            if (border) {
+                for (int i = tid; i < n_fix; i += kSweepThreads) {
+                    const uint32_t e = fixlist[i];
+                    sm[e >> 16] = sm[e & 0xffffu];
+                }
+                fence_proxy_async_smem();  // these generic writes precede a later TMA refill of the stage
+                __syncthreads();
             }
+
+            float a0 = 0.f, a1 = 0.f;
+            const float* sp = sm + sbase;
+#pragma unroll
+            for (int di = 0; di < D; ++di) {
+                const int d = DS::kStatic ? DS::get(di) : dil.d[di];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int dy = (j < 3) ? -1 : ((j < 5) ? 0 : 1);
+                    const int dx = (j < 3) ? (j - 1) : ((j == 3) ? -1 : ((j == 4) ? 1 : (j - 6)));
+                    const int off = dy * d * kBox + dx * d;
+                    a0 = fmaf(w0[di * 8 + j], sp[off], a0);
+                    a1 = fmaf(w1[di * 8 + j], sp[off + kRowGap * kBox], a1);
+                }
+            }
+            if (valid0) out0[(size_t)c * HW] = a0;
+            if (valid1) out0[(size_t)c * HW + (size_t)kRowGap * W] = a1;
+
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);  // this warp no longer reads the stage
         }
-        if (valid0) out0[(size_t)c * HW] = a0;
-        if (valid1) out0[(size_t)c * HW + (size_t)16 * W] = a1;
     }
 }
 
