@@ -232,6 +232,9 @@ def main():
 
     # ---- device-resident timing: K steps, CUDA events, barrier + sync on both sides
     sweep_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K_)]
+    for a, b in sweep_ev:  # create the CUDA events now; the library re-records them around the sweeps
+        a.record()
+        b.record()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks = ClockSampler(local)
     cdist.barrier()

@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcl4wsis_b200.so")
+LIB_PATH = os.environ.get("CL4_LIB") or os.path.join(_HERE, "libcl4wsis_b200.so")  # CL4_LIB: A/B variant builds
 
 CL4_OK, CL4_EINVAL, CL4_EUNSUPPORTED, CL4_ECUDA, CL4_ESCRATCH = 0, -1, -2, -3, -4
 MAX_DILATIONS = 8
@@ -30,6 +30,8 @@ SIGNATURES = {
     "cl4_pamr_scratch_bytes": (_sz, [_int] * 7),
     "cl4_pamr_forward": (_int, [_vp, _vp, _vp, _vp, _sz, _int, _int, _int, _int, _int, ctypes.POINTER(_int), _int,
                                 _int, _vp]),
+    "cl4_pamr_forward_timed": (_int, [_vp, _vp, _vp, _vp, _sz, _int, _int, _int, _int, _int, ctypes.POINTER(_int),
+                                      _int, _int, _vp, _vp, _vp]),
     "cl4_peak_extract_scratch_bytes": (_sz, [_int] * 6),
     "cl4_peak_extract": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _int, _int, _int, _int, _int, _int, _vp]),
     "cl4_center_nms_scratch_bytes": (_sz, [_int] * 3),

@@ -33,10 +33,16 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra=None, lib=None):
+    """``extra``: additional nvcc flags (A/B experiments, e.g. ["-DCL4_SWEEP_STAGES=6"]);
+    ``lib``: alternative output path for such a variant (objects are rebuilt)."""
+    extra = list(extra or []) + os.environ.get("CL4_NVCC_EXTRA", "").split()
+    if extra:
+        force = True
+    out_lib = lib or LIB
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(ROOT, "include", "cl4wsis_b200.h"))
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if not lib else "build_variant")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     objs, procs = [], []
@@ -45,9 +51,9 @@ def build(force=False, verbose=False):
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc, "-c", s, "-o", o] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+            cmd = [nvcc, "-c", s, "-o", o] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else [])
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    relink = force or bool(procs) or _stale(LIB, objs)
+    relink = force or bool(procs) or _stale(out_lib, objs)
     for src, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:
@@ -55,9 +61,9 @@ def build(force=False, verbose=False):
         if verbose or "warning" in out:
             sys.stderr.write(out)
     if relink:
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        cmd = [nvcc, "-shared", "-o", out_lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
         subprocess.check_call(cmd)
-    return LIB
+    return out_lib
 
 
 if __name__ == "__main__":

@@ -40,7 +40,8 @@ __global__ void resize_bilinear_ac_kernel(const float* __restrict__ in, float* _
 // ---------------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(256)
-pamr_weights_kernel(const float* __restrict__ img, float* __restrict__ wts, int K, int H, int W, Dilations dil) {
+pamr_weights_kernel(const float* __restrict__ img, float* __restrict__ wts, int K, int H, int W, Dilations dil,
+                    int tiled) {
     constexpr int P = 8 * D;
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
@@ -97,9 +98,19 @@ pamr_weights_kernel(const float* __restrict__ img, float* __restrict__ wts, int 
         logit[p] = expf(logit[p] - mx);
         z += logit[p];
     }
-    float* o = wts + (size_t)b * P * HW + (size_t)y * W + x;
+    // planar [B,P,H,W] (public layout) or tile-major [tile][P][32][32] (what the TMA sweep reads)
+    float* o;
+    size_t pstride;
+    if (tiled) {
+        const size_t tile = ((size_t)b * gridDim.y / 4 + (y >> 5)) * gridDim.x + blockIdx.x;
+        o = wts + tile * ((size_t)P * 1024) + (y & 31) * 32 + threadIdx.x;
+        pstride = 1024;
+    } else {
+        o = wts + (size_t)b * P * HW + (size_t)y * W + x;
+        pstride = HW;
+    }
 #pragma unroll
-    for (int p = 0; p < P; ++p) o[(size_t)p * HW] = __fdiv_rn(logit[p], z);
+    for (int p = 0; p < P; ++p) o[(size_t)p * pstride] = __fdiv_rn(logit[p], z);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -161,9 +172,10 @@ static int dispatch_D(int D, Args... args) {
 
 template <int D>
 struct WeightsLauncher {
-    static int run(const float* img, float* w, int B, int K, int H, int W, Dilations dil, cudaStream_t s) {
-        dim3 grid(ceil_div(W, 32), ceil_div(H, 8), B);
-        pamr_weights_kernel<D><<<grid, dim3(32, 8), 0, s>>>(img, w, K, H, W, dil);
+    static int run(const float* img, float* w, int B, int K, int H, int W, Dilations dil, int tiled, cudaStream_t s) {
+        // grid.y covers whole 32-row tiles (4 blocks of 8 rows each) so that tile indices are exact
+        dim3 grid(ceil_div(W, 32), ceil_div(H, 32) * 4, B);
+        pamr_weights_kernel<D><<<grid, dim3(32, 8), 0, s>>>(img, w, K, H, W, dil, tiled);
         return check_launch("pamr_weights");
     }
 };
@@ -223,7 +235,7 @@ extern "C" int cl4_pamr_weights(const float* img, float* w, int B, int K, int H,
     if (rc != CL4_OK) return rc;
     if (B == 0) return CL4_OK;
     CL4_REQUIRE(img && w, CL4_EINVAL, "pamr_weights: null pointer");
-    return dispatch_D<WeightsLauncher>(D, img, w, B, K, H, W, dil, (cudaStream_t)stream);
+    return dispatch_D<WeightsLauncher>(D, img, w, B, K, H, W, dil, 0, (cudaStream_t)stream);
 }
 
 extern "C" int cl4_pamr_sweep(const float* w, const float* mask_in, float* mask_out, int B, int C, int H, int W,
@@ -238,11 +250,6 @@ extern "C" int cl4_pamr_sweep(const float* w, const float* mask_in, float* mask_
     if (rc != CL4_OK) return rc;
     if (B == 0) return CL4_OK;
     CL4_REQUIRE(w && mask_in && mask_out && mask_in != mask_out, CL4_EINVAL, "pamr_sweep: null or aliased pointers");
-    // CL4_SWEEP=v1 forces the register/L1 kernel (used by tests and A/B timing)
-    const char* force = getenv("CL4_SWEEP");
-    const bool want_tma = !(force && strcmp(force, "v1") == 0);
-    if (want_tma && D <= 6 && sweep_tma_applicable(C, H, W, dil, D, mask_in))
-        return launch_sweep_tma(w, mask_in, mask_out, B, C, H, W, dil, D, (cudaStream_t)stream);
     return dispatch_D<SweepLauncher>(D, w, mask_in, mask_out, B, C, H, W, dil, (cudaStream_t)stream);
 }
 
@@ -250,43 +257,91 @@ extern "C" size_t cl4_pamr_scratch_bytes(int B, int K, int C, int H, int W, int 
     (void)K;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return 0;
     const size_t HW = (size_t)H * W;
-    const size_t wbytes = cl4::align_up(sizeof(float) * (size_t)B * 8 * D * HW, 256);
-    const size_t mbytes = (num_iter >= 2) ? cl4::align_up(sizeof(float) * (size_t)B * C * HW, 256) : 0;
-    return wbytes + mbytes;
+    (void)HW;
+    const size_t wbytes = cl4::align_up(sizeof(float) * cl4::tiled_weight_elems(B, H, W, D), 256);
+    // padded path: one replicate-padded copy of the input (+ a second ping-pong buffer from 2 sweeps on);
+    // generic path: one plain ping-pong buffer.  The padded layout is the larger of the two.
+    const size_t padded = cl4::align_up(sizeof(float) * (size_t)B * C * cl4::padded_plane_elems(H, W), 256);
+    return wbytes + (num_iter >= 2 ? 2 : 1) * padded;
+}
+
+extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, float* mask_out, void* scratch,
+                                      size_t scratch_bytes, int B, int K, int C, int H, int W, const int* dilations,
+                                      int D, int num_iter, cl4_stream_t stream, cl4_event_t ev_sweeps_begin,
+                                      cl4_event_t ev_sweeps_end) {
+    using namespace cl4;
+    int rc = check_plane("pamr_forward", B, H, W);
+    if (rc != CL4_OK) return rc;
+    CL4_REQUIRE(K >= 1 && C >= 1 && num_iter >= 0, CL4_EINVAL, "pamr_forward: bad K/C/num_iter");
+    CL4_REQUIRE((long long)C * H * W < (1ll << 31), CL4_EUNSUPPORTED, "pamr_forward: C*H*W too large");
+    Dilations dil;
+    rc = make_dilations(dilations, D, &dil);
+    if (rc != CL4_OK) return rc;
+    if (B == 0) return CL4_OK;
+    CL4_REQUIRE(img && mask_in && mask_out && mask_in != mask_out, CL4_EINVAL, "pamr_forward: null or aliased pointers");
+    const size_t HW = (size_t)H * W;
+    cudaStream_t s = (cudaStream_t)stream;
+    auto record = [&](cl4_event_t ev) -> int {
+        if (!ev) return CL4_OK;
+        cudaError_t e = cudaEventRecord((cudaEvent_t)ev, s);
+        CL4_REQUIRE(e == cudaSuccess, CL4_ECUDA, "pamr_forward: event record: %s", cudaGetErrorString(e));
+        return CL4_OK;
+    };
+    if (num_iter == 0) {
+        cudaError_t e = cudaMemcpyAsync(mask_out, mask_in, sizeof(float) * (size_t)B * C * HW, cudaMemcpyDeviceToDevice, s);
+        CL4_REQUIRE(e == cudaSuccess, CL4_ECUDA, "pamr_forward: copy: %s", cudaGetErrorString(e));
+        if ((rc = record(ev_sweeps_begin)) != CL4_OK) return rc;
+        return record(ev_sweeps_end);
+    }
+    CL4_REQUIRE(scratch && scratch_bytes >= cl4_pamr_scratch_bytes(B, K, C, H, W, D, num_iter), CL4_ESCRATCH,
+                "pamr_forward: scratch too small");
+    char* base = reinterpret_cast<char*>(scratch);
+    float* wts = reinterpret_cast<float*>(base);
+    const size_t wbytes = align_up(sizeof(float) * tiled_weight_elems(B, H, W, D), 256);
+    const size_t padded = align_up(sizeof(float) * (size_t)B * C * padded_plane_elems(H, W), 256);
+    float* bufA = reinterpret_cast<float*>(base + wbytes);
+    float* bufB = reinterpret_cast<float*>(base + wbytes + padded);
+    // CL4_SWEEP=v1 forces the register/L1 kernel (A/B timing and tests of the generic path)
+    const char* force = getenv("CL4_SWEEP");
+    const bool use_tma = !(force && strcmp(force, "v1") == 0) && sweep_tma_applicable(H, W, dil, D);
+    rc = dispatch_D<WeightsLauncher>(D, img, wts, B, K, H, W, dil, use_tma ? 1 : 0, s);
+    if (rc != CL4_OK) return rc;
+    if (use_tma) {
+        // replicate-padded ping-pong: in -> A -> B -> A ... -> out (plain layout)
+        const long long planes = (long long)B * C;
+        rc = launch_pad_copy(mask_in, bufA, planes, H, W, s);
+        if (rc != CL4_OK) return rc;
+        if ((rc = record(ev_sweeps_begin)) != CL4_OK) return rc;
+        float* cur = bufA;
+        float* nxt = bufB;
+        for (int it = 0; it < num_iter; ++it) {
+            const bool last = (it == num_iter - 1);
+            rc = launch_sweep_tma(wts, cur, last ? mask_out : nxt, last ? 0 : 1, B, C, H, W, dil, D, s);
+            if (rc != CL4_OK) return rc;
+            if (!last) {
+                rc = launch_pad_refresh(nxt, planes, H, W, s);
+                if (rc != CL4_OK) return rc;
+                float* t = cur; cur = nxt; nxt = t;
+            }
+        }
+        return record(ev_sweeps_end);
+    }
+    // generic path: plain ping-pong so that the last sweep lands in mask_out
+    if ((rc = record(ev_sweeps_begin)) != CL4_OK) return rc;
+    const float* cur = mask_in;
+    for (int it = 0; it < num_iter; ++it) {
+        const int remaining = num_iter - it;  // sweeps left including this one
+        float* dst = (remaining & 1) ? mask_out : bufA;
+        rc = cl4_pamr_sweep(wts, cur, dst, B, C, H, W, dilations, D, stream);
+        if (rc != CL4_OK) return rc;
+        cur = dst;
+    }
+    return record(ev_sweeps_end);
 }
 
 extern "C" int cl4_pamr_forward(const float* img, const float* mask_in, float* mask_out, void* scratch,
                                 size_t scratch_bytes, int B, int K, int C, int H, int W, const int* dilations, int D,
                                 int num_iter, cl4_stream_t stream) {
-    using namespace cl4;
-    int rc = check_plane("pamr_forward", B, H, W);
-    if (rc != CL4_OK) return rc;
-    CL4_REQUIRE(K >= 1 && C >= 1 && num_iter >= 0, CL4_EINVAL, "pamr_forward: bad K/C/num_iter");
-    if (B == 0) return CL4_OK;
-    CL4_REQUIRE(img && mask_in && mask_out && mask_in != mask_out, CL4_EINVAL, "pamr_forward: null or aliased pointers");
-    const size_t HW = (size_t)H * W;
-    const size_t nmask = sizeof(float) * (size_t)B * C * HW;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (num_iter == 0) {
-        cudaError_t e = cudaMemcpyAsync(mask_out, mask_in, nmask, cudaMemcpyDeviceToDevice, s);
-        CL4_REQUIRE(e == cudaSuccess, CL4_ECUDA, "pamr_forward: copy: %s", cudaGetErrorString(e));
-        return CL4_OK;
-    }
-    CL4_REQUIRE(scratch && scratch_bytes >= cl4_pamr_scratch_bytes(B, K, C, H, W, D, num_iter), CL4_ESCRATCH,
-                "pamr_forward: scratch too small");
-    float* wts = reinterpret_cast<float*>(scratch);
-    float* tmp = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) +
-                                          align_up(sizeof(float) * (size_t)B * 8 * D * HW, 256));
-    rc = cl4_pamr_weights(img, wts, B, K, H, W, dilations, D, stream);
-    if (rc != CL4_OK) return rc;
-    // ping-pong so that the last sweep lands in mask_out: in -> (tmp|out) -> ... -> out
-    const float* cur = mask_in;
-    for (int it = 0; it < num_iter; ++it) {
-        const int remaining = num_iter - it;  // sweeps left including this one
-        float* dst = (remaining & 1) ? mask_out : tmp;
-        rc = cl4_pamr_sweep(wts, cur, dst, B, C, H, W, dilations, D, stream);
-        if (rc != CL4_OK) return rc;
-        cur = dst;
-    }
-    return CL4_OK;
+    return cl4_pamr_forward_timed(img, mask_in, mask_out, scratch, scratch_bytes, B, K, C, H, W, dilations, D, num_iter,
+                                  stream, nullptr, nullptr);
 }

@@ -4,10 +4,18 @@
 
 namespace cl4 {
 
-// TMA-staged sweep (pamr_tma.cu).  Applicable when W % 4 == 0, the map has at least 32x32
-// pixels and every dilation is <= 24; otherwise the register/L1 kernel in pamr.cu is used.
-bool sweep_tma_applicable(int C, int H, int W, const Dilations& dil, int D, const float* mask_in);
-int launch_sweep_tma(const float* w, const float* mi, float* mo, int B, int C, int H, int W, const Dilations& dil,
-                     int D, cudaStream_t s);
+constexpr int kPamrPad = 24;  // frame of the replicate-padded mask planes = largest dilation of the TMA path
+
+// TMA-staged sweep over replicate-padded planes (pamr_tma.cu).  Applicable when W % 4 == 0, the
+// map has at least 32x32 pixels, D <= 6 and every dilation is <= 24; otherwise the register/L1
+// kernel in pamr.cu is used.
+bool sweep_tma_applicable(int H, int W, const Dilations& dil, int D);
+size_t padded_plane_elems(int H, int W);
+size_t tiled_weight_elems(int B, int H, int W, int D);  // weights in [tile][8D][32][32] layout (>= B*8D*H*W)
+int launch_pad_copy(const float* src, float* dst, long long planes, int H, int W, cudaStream_t s);
+int launch_pad_refresh(float* buf, long long planes, int H, int W, cudaStream_t s);
+// w: tile-major weights (tiled_weight_elems), as written by the weights kernel in tiled mode
+int launch_sweep_tma(const float* w, const float* padded_in, float* out, int out_padded, int B, int C, int H, int W,
+                     const Dilations& dil, int D, cudaStream_t s);
 
 }  // namespace cl4

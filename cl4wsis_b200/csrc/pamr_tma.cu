@@ -1,13 +1,23 @@
 // PAMR propagation sweep, TMA-staged (reference wss/modules.py:148-149).
 //
-// One persistent CTA per SM walks over 32x32-pixel output tiles (image-major order, so
-// neighbouring CTAs share halos in L2).  For a tile, every thread keeps the 8*D affinity
-// weights of its two pixels in registers for all C classes; per class the 80x80 source window
-// (tile + 24-pixel halo) is brought into shared memory by ONE cp.async.bulk.tensor (TMA) box
-// load, triple-buffered on mbarriers so that the copy of class c+2 overlaps the FMAs of class c.
-// TMA zero-fills outside the image; tiles that touch the border then rewrite those cells with
-// the clamped (replicate-padded, wss/modules.py:57) values, which are in the same window.
-// The inner loop is one LDS + one FFMA per (pixel, tap) with compile-time shared-memory offsets.
+// Layout.  Between sweeps the masks live in HBM as REPLICATE-PADDED planes
+// [B*C][H+48][W+48] (24 = largest dilation): the clamped neighbour of wss/modules.py:57 is then
+// an ordinary in-bounds read, every 80x80 source window is a plain TMA box and the hot loop has
+// no border case.  A small kernel refreshes the 24-pixel frame after each sweep.
+//
+// Sweep kernel.  One persistent CTA per SM (256 threads) walks over 32x32-pixel output tiles in
+// image-major order (neighbouring CTAs share halos in L2).  A thread owns four pixels of one
+// column, 4 rows apart, and keeps their 4 x 8D affinity weights in registers for all C classes
+// of the tile (the weights are the only per-pixel state; 192 registers at D = 6).  Per class the
+// 80x80 window arrives by ONE cp.async.bulk.tensor box load into a 6-stage shared-memory ring
+// guarded by full/empty mbarriers, so the copies of the next five classes overlap the FMAs.
+// The inner loop is LDS (immediate offset) + FFMA; because the four pixels sit 4 rows apart,
+// 39 of their 192 (pixel, tap) sources coincide and are loaded once (153 LDS per 192 FFMA) —
+// the loop is bound by shared-memory bandwidth (one 128-byte wavefront per cycle), not by FP32.
+// While the last class of a tile is computed, each weight register is refilled with the next
+// tile's value right after its final use, which hides the 196 KB weight fetch.  The weights are
+// stored tile-major ([tile][p][32][32], written by the weights kernel), so all 192 loads of a
+// thread are immediate offsets from one pointer.
 #include "common.cuh"
 #include "pamr_internal.cuh"
 #include "tma.cuh"
@@ -15,16 +25,16 @@
 namespace cl4 {
 
 constexpr int kTile = 32;
-constexpr int kHalo = 24;                       // largest supported dilation on this path
+constexpr int kHalo = kPamrPad;                 // 24: largest supported dilation on this path
 constexpr int kBox = kTile + 2 * kHalo;         // 80
-constexpr int kStages = 4;
-constexpr int kSweepThreads = 512;              // 16 warps; each thread owns two pixels 8 rows apart
-constexpr int kRowGap = 8;                      // (y, y+8): the d=8 and d=4 taps of the pair share 7 sources
+constexpr int kStages = 6;
+constexpr int kSweepThreads = 256;              // 8 warps; warp (h,q) owns rows h*16 + q + 4*i, i = 0..3
+constexpr int kPx = 4;                          // pixels per thread
+constexpr int kRowGap = 4;
 constexpr int kStageBytes = kBox * kBox * 4;    // 25600
-constexpr int kMaxFix = kBox * kBox - 1;        // out-of-image cells of a window (always < box area)
-constexpr size_t kSweepSmem = (size_t)kStages * kStageBytes + (size_t)kMaxFix * 4 + 128;
+constexpr size_t kSweepSmem = (size_t)kStages * kStageBytes + 128;
 
-// compile-time dilation sets get immediate LDS offsets; RuntimeDil keeps them in registers
+// compile-time dilation sets get immediate LDS offsets; DilRuntime computes them from registers
 struct DilVoc6 {  // PAMR's class default (wss/modules.py:125)
     static constexpr bool kStatic = true;
     __host__ __device__ static constexpr int get(int i) {
@@ -55,24 +65,50 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int tiles_x, int tiles_pe
     return tc;
 }
 
+struct SweepOut {
+    float* ptr;           // element (plane 0, y = 0, x = 0) of the output
+    long long plane;      // elements between planes
+    int pitch;            // elements between rows
+};
+
+// One class of one tile.  kReload: refill every weight register with the next tile's weight
+// right after its last use (software-pipelined fetch, no extra registers).
+template <int D, class DS, bool kReload>
+__device__ __forceinline__ void sweep_class(float (&w)[kPx][8 * D], const float* __restrict__ sp, const Dilations& dil,
+                                            const float* __restrict__ nw, float (&acc)[kPx]) {
+#pragma unroll
+    for (int i = 0; i < kPx; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int di = 0; di < D; ++di) {
+        const int d = DS::kStatic ? DS::get(di) : dil.d[di];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int dy = (j < 3) ? -1 : ((j < 5) ? 0 : 1);
+            const int dx = (j < 3) ? (j - 1) : ((j == 3) ? -1 : ((j == 4) ? 1 : (j - 6)));
+            const int off = dy * d * kBox + dx * d;
+#pragma unroll
+            for (int i = 0; i < kPx; ++i) {
+                acc[i] = fmaf(w[i][di * 8 + j], sp[off + i * kRowGap * kBox], acc[i]);
+                if (kReload) w[i][di * 8 + j] = __ldg(nw + (di * 8 + j) * (kTile * kTile) + i * kRowGap * kTile);
+            }
+        }
+    }
+}
+
 template <int D, class DS>
 __global__ void __launch_bounds__(kSweepThreads, 1)
-pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wts,
-                      float* __restrict__ mout, int C, int H, int W, int tiles_x, int tiles_y, int n_tiles,
-                      Dilations dil) {
+pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wts, SweepOut out, int C,
+                      int H, int W, int tiles_x, int tiles_y, int n_tiles, Dilations dil) {
     constexpr int P = 8 * D;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* stage0 = reinterpret_cast<float*>(smem_raw);
-    uint32_t* fixlist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kStages * kStageBytes);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageBytes + (size_t)kMaxFix * 4 + 4);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageBytes);
     uint64_t* empty = full + kStages;
-    __shared__ int s_nfix;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, wrp = tid >> 5;
     const int tx = lane;
-    const int ty = (wrp >> 3) * 16 + (wrp & 7);  // rows ty and ty + kRowGap
-    const size_t HW = (size_t)H * W;
+    const int ty = (wrp >> 2) * 16 + (wrp & 3);  // rows ty + 4*i
     const int tiles_per_img = tiles_x * tiles_y;
 
     // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
@@ -90,7 +126,8 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
     }
     __syncthreads();
 
-    // ---- producer (thread 0 only): p_item is the next (tile, class) item to issue
+    // ---- producer (thread 0 only): p_item is the next (tile, class) item to issue.  The padded
+    // plane holds pixel (y, x) at (y + 24, x + 24), so the window of tile (y0, x0) starts at (y0, x0).
     int p_item = 0;
     auto issue_next = [&]() {
         const int pk = p_item / C, pc = p_item - pk * C;
@@ -98,98 +135,112 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
         const int s = p_item % kStages;
         if (p_item >= kStages) mbar_wait(&empty[s], (uint32_t)((p_item / kStages - 1) & 1));
         mbar_arrive_expect_tx(&full[s], kStageBytes);
-        tma_load_3d(stage0 + (size_t)s * (kBox * kBox), &tmap, &full[s], ptc.x0 - kHalo, ptc.y0 - kHalo,
-                    ptc.b * C + pc);
+        tma_load_3d(stage0 + (size_t)s * (kBox * kBox), &tmap, &full[s], ptc.x0, ptc.y0, ptc.b * C + pc);
         ++p_item;
     };
     if (tid == 0) {
         for (int i = 0; i < kStages - 1 && p_item < total; ++i) issue_next();
     }
 
-    float w0[P], w1[P];
+    float w[kPx][P];
+    float acc[kPx];
     const int sbase = (ty + kHalo) * kBox + (tx + kHalo);
     int item = 0;
 
-    for (int k = 0; k < n_my; ++k) {
-        const TileCoord tc = tile_coord(blockIdx.x + k * gridDim.x, tiles_x, tiles_per_img);
-        const int x = tc.x0 + tx, ya = tc.y0 + ty;
-        const bool valid0 = (x < W) && (ya < H);
-        const bool valid1 = (x < W) && (ya + kRowGap < H);
-        const bool border = (tc.x0 < kHalo) || (tc.y0 < kHalo) || (tc.x0 + kTile + kHalo > W) ||
-                            (tc.y0 + kTile + kHalo > H);
-        {  // weights of this thread's two pixels, kept in registers for all classes of the tile
-            const float* wp = wts + (size_t)tc.b * P * HW + (size_t)ya * W + x;
+    auto valid_mask = [&](const TileCoord& tc) -> unsigned {
+        unsigned m = 0;
+        const int x = tc.x0 + tx;
 #pragma unroll
-            for (int p = 0; p < P; ++p) {
-                w0[p] = valid0 ? __ldg(wp + (size_t)p * HW) : 0.f;
-                w1[p] = valid1 ? __ldg(wp + (size_t)p * HW + (size_t)kRowGap * W) : 0.f;
-            }
+        for (int i = 0; i < kPx; ++i)
+            if (x < W && tc.y0 + ty + i * kRowGap < H) m |= 1u << i;
+        return m;
+    };
+    // tile-major weights: tile t holds [P][32][32]; pixels outside the image are never stored,
+    // so whatever sits in their slots is loaded but unused
+    auto weight_ptr = [&](int t) -> const float* {
+        return wts + (size_t)t * (P * kTile * kTile) + ty * kTile + tx;
+    };
+
+    TileCoord tc = tile_coord(blockIdx.x, tiles_x, tiles_per_img);
+    unsigned valid = (n_my > 0) ? valid_mask(tc) : 0u;
+    if (n_my > 0) {  // first tile: plain weight fetch
+        const float* wp = weight_ptr(blockIdx.x);
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+#pragma unroll
+            for (int i = 0; i < kPx; ++i) w[i][p] = __ldg(wp + p * (kTile * kTile) + i * kRowGap * kTile);
+    }
+
+    for (int k = 0; k < n_my; ++k) {
+        const bool has_next = (k + 1 < n_my);
+        TileCoord ntc = tc;
+        unsigned nvalid = 0u;
+        const float* nwp = wts;
+        if (has_next) {
+            ntc = tile_coord(blockIdx.x + (k + 1) * gridDim.x, tiles_x, tiles_per_img);
+            nvalid = valid_mask(ntc);
+            nwp = weight_ptr(blockIdx.x + (k + 1) * gridDim.x);
         }
-        if (k + 1 < n_my) {  // pull the next tile's weights (P planes x 32 rows x 128 B) into L2
-            const TileCoord nt = tile_coord(blockIdx.x + (k + 1) * gridDim.x, tiles_x, tiles_per_img);
-            const float* nb = wts + (size_t)nt.b * P * HW + (size_t)nt.y0 * W + nt.x0;
-            for (int i = tid; i < P * kTile; i += kSweepThreads) {
-                const int p = i >> 5, r = i & 31;
-                if (nt.y0 + r < H) prefetch_l2(nb + (size_t)p * HW + (size_t)r * W);
-            }
-        }
-        int n_fix = 0;
-        if (border) {
-            // Replicate padding (wss/modules.py:57): list the window cells that fall outside the
-            // image together with the in-image cell they copy; the list is reused for every class.
-            if (tid == 0) s_nfix = 0;
-            __syncthreads();
-            for (int i = tid; i < kBox * kBox; i += kSweepThreads) {
-                const int by = i / kBox, bx = i - by * kBox;
-                const int gy = tc.y0 - kHalo + by, gx = tc.x0 - kHalo + bx;
-                const int cy = clampi(gy, 0, H - 1), cx = clampi(gx, 0, W - 1);
-                if (cy != gy || cx != gx) {
-                    const int src = (cy - (tc.y0 - kHalo)) * kBox + (cx - (tc.x0 - kHalo));
-                    fixlist[atomicAdd(&s_nfix, 1)] = ((uint32_t)i << 16) | (uint32_t)src;
-                }
-            }
-            __syncthreads();
-            n_fix = s_nfix;
-        }
-        float* out0 = mout + (size_t)tc.b * C * HW + (size_t)ya * W + x;
+        float* o = out.ptr + (long long)tc.b * C * out.plane + (long long)(tc.y0 + ty) * out.pitch + (tc.x0 + tx);
 
         for (int c = 0; c < C; ++c, ++item) {
             if (tid == 0 && p_item < total) issue_next();  // refills the stage released by item-1
 
             const int s = item % kStages;
-            float* sm = stage0 + (size_t)s * (kBox * kBox);
+            const float* sp = stage0 + (size_t)s * (kBox * kBox) + sbase;
             mbar_wait(&full[s], (uint32_t)((item / kStages) & 1));
 
-            if (border) {
-                for (int i = tid; i < n_fix; i += kSweepThreads) {
-                    const uint32_t e = fixlist[i];
-                    sm[e >> 16] = sm[e & 0xffffu];
-                }
-                fence_proxy_async_smem();  // these generic writes precede a later TMA refill of the stage
-                __syncthreads();
-            }
+            if (c == C - 1 && has_next)
+                sweep_class<D, DS, true>(w, sp, dil, nwp, acc);
+            else
+                sweep_class<D, DS, false>(w, sp, dil, nwp, acc);
 
-            float a0 = 0.f, a1 = 0.f;
-            const float* sp = sm + sbase;
 #pragma unroll
-            for (int di = 0; di < D; ++di) {
-                const int d = DS::kStatic ? DS::get(di) : dil.d[di];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int dy = (j < 3) ? -1 : ((j < 5) ? 0 : 1);
-                    const int dx = (j < 3) ? (j - 1) : ((j == 3) ? -1 : ((j == 4) ? 1 : (j - 6)));
-                    const int off = dy * d * kBox + dx * d;
-                    a0 = fmaf(w0[di * 8 + j], sp[off], a0);
-                    a1 = fmaf(w1[di * 8 + j], sp[off + kRowGap * kBox], a1);
-                }
-            }
-            if (valid0) out0[(size_t)c * HW] = a0;
-            if (valid1) out0[(size_t)c * HW + (size_t)kRowGap * W] = a1;
+            for (int i = 0; i < kPx; ++i)
+                if ((valid >> i) & 1u) o[(long long)c * out.plane + (long long)(i * kRowGap) * out.pitch] = acc[i];
 
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);  // this warp no longer reads the stage
         }
+        tc = ntc;
+        valid = nvalid;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Replicate-padded planes.
+// ---------------------------------------------------------------------------------------------
+// dst [planes][H+2*pad][W+2*pad] <- replicate-pad(src [planes][H][W])
+__global__ void pamr_pad_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W) {
+    const int Wp = W + 2 * kHalo, Hp = H + 2 * kHalo;
+    const int xp = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yp = blockIdx.y * blockDim.y + threadIdx.y;
+    if (xp >= Wp || yp >= Hp) return;
+    const int y = clampi(yp - kHalo, 0, H - 1), x = clampi(xp - kHalo, 0, W - 1);
+    dst[((size_t)blockIdx.z * Hp + yp) * Wp + xp] = __ldg(src + ((size_t)blockIdx.z * H + y) * W + x);
+}
+
+// In place: frame cells of a padded plane <- nearest interior cell.  One thread per frame cell:
+// the frame is 2*pad full rows (top/bottom) + H rows x 2*pad columns (left/right).
+__global__ void pamr_pad_refresh_kernel(float* __restrict__ buf, int H, int W) {
+    const int Wp = W + 2 * kHalo, Hp = H + 2 * kHalo;
+    float* pl = buf + (size_t)blockIdx.y * Hp * Wp;
+    const int n_rows_part = 2 * kHalo * Wp;  // top and bottom bands
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int yp, xp;
+    if (i < n_rows_part) {
+        const int r = i / Wp;
+        xp = i - r * Wp;
+        yp = (r < kHalo) ? r : (H + r);  // r in [24,48) -> rows H+24 .. H+47
+    } else {
+        const int j = i - n_rows_part;
+        if (j >= H * 2 * kHalo) return;
+        const int r = j / (2 * kHalo), cidx = j - r * (2 * kHalo);
+        yp = r + kHalo;
+        xp = (cidx < kHalo) ? cidx : (W + cidx);
+    }
+    const int ys = clampi(yp, kHalo, H + kHalo - 1), xs = clampi(xp, kHalo, W + kHalo - 1);
+    pl[(size_t)yp * Wp + xp] = pl[(size_t)ys * Wp + xs];
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -222,18 +273,37 @@ int encode_tmap_3d_f32(CUtensorMap* map, const float* base, int W, int H, long l
     return (int)r;
 }
 
-bool sweep_tma_applicable(int C, int H, int W, const Dilations& dil, int D, const float* mask_in) {
-    if (W % 4 != 0 || ((uintptr_t)mask_in & 15) != 0) return false;  // TMA: 16-byte global strides / base
-    if ((long long)H * W < 32 * 32) return false;                    // tiny maps: the register kernel is fine
-    (void)C;
+bool sweep_tma_applicable(int H, int W, const Dilations& dil, int D) {
+    if (D > 6) return false;                       // 4 x 8D weight registers per thread
+    if (W % 4 != 0) return false;                  // TMA: 16-byte global row pitch
+    if ((long long)H * W < 32 * 32) return false;  // tiny maps: the register/L1 kernel is fine
     for (int i = 0; i < D; ++i)
         if (dil.d[i] > kHalo) return false;
     return true;
 }
 
+size_t tiled_weight_elems(int B, int H, int W, int D) {
+    return (size_t)B * ceil_div(H, kTile) * ceil_div(W, kTile) * (size_t)(8 * D) * kTile * kTile;
+}
+
+size_t padded_plane_elems(int H, int W) { return (size_t)(H + 2 * kHalo) * (size_t)(W + 2 * kHalo); }
+
+int launch_pad_copy(const float* src, float* dst, long long planes, int H, int W, cudaStream_t s) {
+    dim3 block(32, 8), grid(ceil_div(W + 2 * kHalo, 32), ceil_div(H + 2 * kHalo, 8), (unsigned)planes);
+    pamr_pad_copy_kernel<<<grid, block, 0, s>>>(src, dst, H, W);
+    return check_launch("pamr_pad_copy");
+}
+
+int launch_pad_refresh(float* buf, long long planes, int H, int W, cudaStream_t s) {
+    const int cells = 2 * kHalo * (W + 2 * kHalo) + H * 2 * kHalo;
+    dim3 grid(ceil_div(cells, 256), (unsigned)planes);
+    pamr_pad_refresh_kernel<<<grid, 256, 0, s>>>(buf, H, W);
+    return check_launch("pamr_pad_refresh");
+}
+
 template <int D, class DS>
-static int launch_one(const CUtensorMap& tmap, const float* w, float* mo, int C, int H, int W, int tiles_x, int tiles_y,
-                      int n_tiles, const Dilations& dil, cudaStream_t s) {
+static int launch_one(const CUtensorMap& tmap, const float* w, const SweepOut& out, int C, int H, int W, int tiles_x,
+                      int tiles_y, int n_tiles, const Dilations& dil, cudaStream_t s) {
     auto kern = pamr_sweep_tma_kernel<D, DS>;
     static bool attr_done = false;  // per instantiation
     if (!attr_done) {
@@ -245,44 +315,53 @@ static int launch_one(const CUtensorMap& tmap, const float* w, float* mo, int C,
         attr_done = true;
     }
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-    kern<<<grid, kSweepThreads, kSweepSmem, s>>>(tmap, w, mo, C, H, W, tiles_x, tiles_y, n_tiles, dil);
+    kern<<<grid, kSweepThreads, kSweepSmem, s>>>(tmap, w, out, C, H, W, tiles_x, tiles_y, n_tiles, dil);
     return check_launch("pamr_sweep_tma");
 }
 
 template <int D>
-struct TmaSweepLauncher {
-    static int run(const CUtensorMap& tmap, const float* w, float* mo, int C, int H, int W, int tiles_x, int tiles_y,
-                   int n_tiles, const Dilations& dil, cudaStream_t s) {
-        bool voc6 = (D == 6), voc5 = (D == 5);
-        for (int i = 0; i < D && i < 6; ++i) {
-            voc6 = voc6 && dil.d[i] == DilVoc6::get(i);
-            voc5 = voc5 && dil.d[i] == DilVoc5::get(i);
-        }
-        if (D == 6 && voc6) return launch_one<6, DilVoc6>(tmap, w, mo, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
-        if (D == 5 && voc5) return launch_one<5, DilVoc5>(tmap, w, mo, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
-        return launch_one<D, DilRuntime>(tmap, w, mo, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
+static int launch_D(const CUtensorMap& tmap, const float* w, const SweepOut& out, int C, int H, int W, int tiles_x,
+                    int tiles_y, int n_tiles, const Dilations& dil, cudaStream_t s) {
+    bool voc6 = (D == 6), voc5 = (D == 5);
+    for (int i = 0; i < D && i < 6; ++i) {
+        voc6 = voc6 && dil.d[i] == DilVoc6::get(i);
+        voc5 = voc5 && dil.d[i] == DilVoc5::get(i);
     }
-};
+    if (D == 6 && voc6) return launch_one<6, DilVoc6>(tmap, w, out, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
+    if (D == 5 && voc5) return launch_one<5, DilVoc5>(tmap, w, out, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
+    return launch_one<D, DilRuntime>(tmap, w, out, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
+}
 
-int launch_sweep_tma(const float* w, const float* mi, float* mo, int B, int C, int H, int W, const Dilations& dil, int D,
-                     cudaStream_t s) {
+// padded_in: [B*C][H+48][W+48].  out_padded != 0: `out` is a padded buffer of the same shape (its
+// frame is NOT refreshed here); otherwise `out` is the plain [B*C][H][W] tensor.
+int launch_sweep_tma(const float* w, const float* padded_in, float* out, int out_padded, int B, int C, int H, int W,
+                     const Dilations& dil, int D, cudaStream_t s) {
     CUtensorMap tmap;
-    const int rc = encode_tmap_3d_f32(&tmap, mi, W, H, (long long)B * C, kBox, kBox);
+    const int Wp = W + 2 * kHalo, Hp = H + 2 * kHalo;
+    const int rc = encode_tmap_3d_f32(&tmap, padded_in, Wp, Hp, (long long)B * C, kBox, kBox);
     if (rc != 0) {
         set_error("pamr_sweep_tma: cuTensorMapEncodeTiled failed (%d)", rc);
         return CL4_ECUDA;
     }
+    SweepOut so;
+    if (out_padded) {
+        so.ptr = out + (size_t)kHalo * Wp + kHalo;
+        so.plane = (long long)Hp * Wp;
+        so.pitch = Wp;
+    } else {
+        so.ptr = out;
+        so.plane = (long long)H * W;
+        so.pitch = W;
+    }
     const int tiles_x = ceil_div(W, kTile), tiles_y = ceil_div(H, kTile);
     const int n_tiles = B * tiles_x * tiles_y;
     switch (D) {
-        case 1: return TmaSweepLauncher<1>::run(tmap, w, mo, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
-        case 2: return TmaSweepLauncher<2>::run(tmap, w, mo, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
-        case 3: return TmaSweepLauncher<3>::run(tmap, w, mo, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
-        case 4: return TmaSweepLauncher<4>::run(tmap, w, mo, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
-        case 5: return TmaSweepLauncher<5>::run(tmap, w, mo, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
-        case 6: return TmaSweepLauncher<6>::run(tmap, w, mo, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
-        case 7: return TmaSweepLauncher<7>::run(tmap, w, mo, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
-        case 8: return TmaSweepLauncher<8>::run(tmap, w, mo, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
+        case 1: return launch_D<1>(tmap, w, so, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
+        case 2: return launch_D<2>(tmap, w, so, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
+        case 3: return launch_D<3>(tmap, w, so, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
+        case 4: return launch_D<4>(tmap, w, so, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
+        case 5: return launch_D<5>(tmap, w, so, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
+        case 6: return launch_D<6>(tmap, w, so, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
     }
     set_error("pamr_sweep_tma: bad D=%d", D);
     return CL4_EUNSUPPORTED;

@@ -36,8 +36,8 @@ class PseudoLabelStep:
         self.ids = torch.empty((B, H, W), dtype=torch.int64, device=dev)
         self.centers = torch.zeros((B, self.max_centers, 2), dtype=torch.int64, device=dev)
         self.counts = torch.zeros((B,), dtype=torch.int32, device=dev)
-        # launches per step: 1 weights + num_iter sweeps + 2 NMS + 1 grouping
-        self.launches_per_step = 1 + self.num_iter + 2 + 1
+        # launches per step: weights, pad copy, num_iter sweeps, num_iter-1 frame refreshes, 2 NMS, grouping
+        self.launches_per_step = 1 + 1 + self.num_iter + max(self.num_iter - 1, 0) + 2 + 1
 
     def run(self, img, mask, heat, offsets, fg=None, stream=None, sweep_events=None):
         """All arguments are contiguous fp32 CUDA tensors: img [B,K,H,W], mask [B,C,H,W],
@@ -48,25 +48,12 @@ class PseudoLabelStep:
         lib, B, C, H, W = self.lib, self.B, self.C, self.H, self.W
         ts = torch.cuda.current_stream(self.device) if stream is None else stream
         st = _lib.ctypes.c_void_p(ts.cuda_stream)
-        if sweep_events is None:
-            _lib.check(lib.cl4_pamr_forward(_lib.ptr(img), _lib.ptr(mask), _lib.ptr(self.refined),
-                                            _lib.ptr(self.pamr_scratch), self.pamr_bytes, B, self.K, C, H, W,
-                                            self._dil_arr, len(self.dil), self.num_iter, st), "PAMR")
-        else:  # same launches as cl4_pamr_forward, issued one by one so the sweeps can be timed
-            D, HW = len(self.dil), H * W
-            wts = self.pamr_scratch
-            tmp_off = ((4 * B * 8 * D * HW + 255) // 256) * 256
-            w_ptr = _lib.ctypes.c_void_p(wts.data_ptr())
-            tmp_ptr = wts.data_ptr() + tmp_off
-            _lib.check(lib.cl4_pamr_weights(_lib.ptr(img), w_ptr, B, self.K, H, W, self._dil_arr, D, st), "weights")
-            sweep_events[0].record(ts)
-            cur = mask.data_ptr()
-            for it in range(self.num_iter):
-                dst = self.refined.data_ptr() if ((self.num_iter - it) & 1) else tmp_ptr
-                _lib.check(lib.cl4_pamr_sweep(w_ptr, _lib.ctypes.c_void_p(cur), _lib.ctypes.c_void_p(dst), B, C, H, W,
-                                              self._dil_arr, D, st), "sweep")
-                cur = dst
-            sweep_events[1].record(ts)
+        ev0 = ev1 = None
+        if sweep_events is not None:  # CUDA events recorded around the num_iter sweeps on this stream
+            ev0, ev1 = (_lib.ctypes.c_void_p(e.cuda_event) for e in sweep_events)
+        _lib.check(lib.cl4_pamr_forward_timed(_lib.ptr(img), _lib.ptr(mask), _lib.ptr(self.refined),
+                                              _lib.ptr(self.pamr_scratch), self.pamr_bytes, B, self.K, C, H, W,
+                                              self._dil_arr, len(self.dil), self.num_iter, st, ev0, ev1), "PAMR")
         _lib.check(lib.cl4_center_nms(_lib.ptr(heat), self.threshold, 0.0, self.nms_kernel, B, H, W,
                                       _lib.ptr(self.centers), _lib.ptr(self.counts), self.max_centers,
                                       _lib.ptr(self.nms_scratch), self.nms_bytes, st), "center_nms")

@@ -35,6 +35,7 @@ extern "C" {
 #define CL4_MAX_TOPK 256
 
 typedef void* cl4_stream_t; /* cudaStream_t */
+typedef void* cl4_event_t;  /* cudaEvent_t  */
 
 /* ABI version (bumped on any signature change) and last error text. */
 int cl4_abi_version(void);
@@ -64,12 +65,18 @@ int cl4_pamr_sweep(const float* w, const float* mask_in, float* mask_out, int B,
 
 /* Whole PAMR.forward after the resize: weights + num_iter sweeps.
  * img [B,K,H,W], mask_in [B,C,H,W] -> mask_out [B,C,H,W].  scratch must hold
- * cl4_pamr_scratch_bytes(...) bytes (weights + one ping-pong mask buffer).
- * mask_in is not modified; mask_out may not alias mask_in. */
+ * cl4_pamr_scratch_bytes(...) bytes (weights [B,8D,H,W] + up to two replicate-padded
+ * mask buffers [B*C,H+48,W+48]).  mask_in is not modified; mask_out may not alias it.
+ * The _timed variant additionally records the two (nullable) events on `stream`
+ * around the num_iter propagation sweeps, for per-kernel timing. */
 size_t cl4_pamr_scratch_bytes(int B, int K, int C, int H, int W, int D, int num_iter);
 int cl4_pamr_forward(const float* img, const float* mask_in, float* mask_out, void* scratch,
                      size_t scratch_bytes, int B, int K, int C, int H, int W, const int* dilations, int D,
                      int num_iter, cl4_stream_t stream);
+int cl4_pamr_forward_timed(const float* img, const float* mask_in, float* mask_out, void* scratch,
+                           size_t scratch_bytes, int B, int K, int C, int H, int W, const int* dilations, int D,
+                           int num_iter, cl4_stream_t stream, cl4_event_t ev_sweeps_begin,
+                           cl4_event_t ev_sweeps_end);
 
 /* ------------------------------------------------------------------------- *
  * peak_extract — wss/utils.py:3-25.
