@@ -98,19 +98,21 @@ pamr_weights_kernel(const float* __restrict__ img, float* __restrict__ wts, int 
         logit[p] = expf(logit[p] - mx);
         z += logit[p];
     }
-    // planar [B,P,H,W] (public layout) or tile-major [tile][P][32][32] (what the TMA sweep reads)
-    float* o;
-    size_t pstride;
+    // planar [B,P,H,W] (public layout) or tile-major [tile][P/4][32][32][4] (what the TMA sweep reads)
+    const float rz = 1.f;
+    (void)rz;
     if (tiled) {
-        const size_t tile = ((size_t)b * gridDim.y / 4 + (y >> 5)) * gridDim.x + blockIdx.x;
-        o = wts + tile * ((size_t)P * 1024) + (y & 31) * 32 + threadIdx.x;
-        pstride = 1024;
-    } else {
-        o = wts + (size_t)b * P * HW + (size_t)y * W + x;
-        pstride = HW;
-    }
+        const size_t tile = ((size_t)b * (gridDim.y / 4) + (y >> 5)) * gridDim.x + blockIdx.x;
+        float4* o = reinterpret_cast<float4*>(wts) + tile * ((size_t)(P / 4) * 1024) + (y & 31) * 32 + threadIdx.x;
 #pragma unroll
-    for (int p = 0; p < P; ++p) o[(size_t)p * pstride] = __fdiv_rn(logit[p], z);
+        for (int g = 0; g < P / 4; ++g)
+            o[(size_t)g * 1024] = make_float4(__fdiv_rn(logit[4 * g], z), __fdiv_rn(logit[4 * g + 1], z),
+                                              __fdiv_rn(logit[4 * g + 2], z), __fdiv_rn(logit[4 * g + 3], z));
+    } else {
+        float* o = wts + (size_t)b * P * HW + (size_t)y * W + x;
+#pragma unroll
+        for (int p = 0; p < P; ++p) o[(size_t)p * HW] = __fdiv_rn(logit[p], z);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -16,8 +16,8 @@
 // the loop is bound by shared-memory bandwidth (one 128-byte wavefront per cycle), not by FP32.
 // While the last class of a tile is computed, each weight register is refilled with the next
 // tile's value right after its final use, which hides the 196 KB weight fetch.  The weights are
-// stored tile-major ([tile][p][32][32], written by the weights kernel), so all 192 loads of a
-// thread are immediate offsets from one pointer.
+// stored tile-major ([tile][p/4][32][32][4], written by the weights kernel): a thread's 192 weights
+// are 48 float4 loads at immediate offsets from one pointer.
 #include "common.cuh"
 #include "pamr_internal.cuh"
 #include "tma.cuh"
@@ -71,25 +71,41 @@ struct SweepOut {
     int pitch;            // elements between rows
 };
 
-// One class of one tile.  kReload: refill every weight register with the next tile's weight
-// right after its last use (software-pipelined fetch, no extra registers).
+// Tile-major weight layout read by this kernel: [tile][P/4][32 rows][32 cols][4 taps] — the four
+// taps 4g..4g+3 of one pixel are one float4, a warp's load is one contiguous 512-byte run, and a
+// thread fetches its 4 x P weights with P (=48 at D=6) 128-bit loads, few enough to be in flight
+// at once.
+__device__ __forceinline__ size_t tiled_weight_index(size_t tile, int P, int p, int row, int col) {
+    return ((tile * (size_t)(P / 4) + (size_t)(p >> 2)) * (kTile * kTile) + (size_t)row * kTile + col) * 4 + (p & 3);
+}
+
+// One class of one tile.  kReload: refill the weight registers with the next tile's weights
+// right after their last use (software-pipelined fetch, no extra registers).
 template <int D, class DS, bool kReload>
 __device__ __forceinline__ void sweep_class(float (&w)[kPx][8 * D], const float* __restrict__ sp, const Dilations& dil,
-                                            const float* __restrict__ nw, float (&acc)[kPx]) {
+                                            const float4* __restrict__ nw, float (&acc)[kPx]) {
 #pragma unroll
     for (int i = 0; i < kPx; ++i) acc[i] = 0.f;
 #pragma unroll
-    for (int di = 0; di < D; ++di) {
-        const int d = DS::kStatic ? DS::get(di) : dil.d[di];
+    for (int g = 0; g < 2 * D; ++g) {  // groups of four taps
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int q = 0; q < 4; ++q) {
+            const int p = 4 * g + q, di = p >> 3, j = p & 7;
+            const int d = DS::kStatic ? DS::get(di) : dil.d[di];
             const int dy = (j < 3) ? -1 : ((j < 5) ? 0 : 1);
             const int dx = (j < 3) ? (j - 1) : ((j == 3) ? -1 : ((j == 4) ? 1 : (j - 6)));
             const int off = dy * d * kBox + dx * d;
 #pragma unroll
+            for (int i = 0; i < kPx; ++i) acc[i] = fmaf(w[i][p], sp[off + i * kRowGap * kBox], acc[i]);
+        }
+        if (kReload) {
+#pragma unroll
             for (int i = 0; i < kPx; ++i) {
-                acc[i] = fmaf(w[i][di * 8 + j], sp[off + i * kRowGap * kBox], acc[i]);
-                if (kReload) w[i][di * 8 + j] = __ldg(nw + (di * 8 + j) * (kTile * kTile) + i * kRowGap * kTile);
+                const float4 v = __ldg(nw + g * (kTile * kTile) + i * kRowGap * kTile);
+                w[i][4 * g + 0] = v.x;
+                w[i][4 * g + 1] = v.y;
+                w[i][4 * g + 2] = v.z;
+                w[i][4 * g + 3] = v.w;
             }
         }
     }
@@ -126,11 +142,21 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
     }
     __syncthreads();
 
-    // ---- producer (thread 0 only): p_item is the next (tile, class) item to issue.  The padded
-    // plane holds pixel (y, x) at (y + 24, x + 24), so the window of tile (y0, x0) starts at (y0, x0).
+    // Staggered class phase: CTA j starts its first tile at class s0 = j*C/gridDim and finishes that
+    // tile's first s0 classes at the very end.  All CTAs would otherwise cross tile boundaries in
+    // lockstep and fetch 148 x 196 KB of weights at the same instant; with the stagger the weight
+    // traffic is spread evenly over time.  Item i of this CTA is (tile ordinal, class) =
+    // ((i + s0) / C mod n_my, (i + s0) mod C).
+    const int s0 = (int)(((long long)blockIdx.x * C) / gridDim.x);
+
+    // ---- producer (thread 0 only): p_item is the next item to issue.  The padded plane holds pixel
+    // (y, x) at (y + 24, x + 24), so the window of tile (y0, x0) starts at (y0, x0).
     int p_item = 0;
     auto issue_next = [&]() {
-        const int pk = p_item / C, pc = p_item - pk * C;
+        const int v = p_item + s0;
+        int pk = v / C;
+        const int pc = v - pk * C;
+        if (pk == n_my) pk = 0;
         const TileCoord ptc = tile_coord(blockIdx.x + pk * gridDim.x, tiles_x, tiles_per_img);
         const int s = p_item % kStages;
         if (p_item >= kStages) mbar_wait(&empty[s], (uint32_t)((p_item / kStages - 1) & 1));
@@ -145,65 +171,82 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
     float w[kPx][P];
     float acc[kPx];
     const int sbase = (ty + kHalo) * kBox + (tx + kHalo);
-    int item = 0;
 
-    auto valid_mask = [&](const TileCoord& tc) -> unsigned {
-        unsigned m = 0;
-        const int x = tc.x0 + tx;
-#pragma unroll
-        for (int i = 0; i < kPx; ++i)
-            if (x < W && tc.y0 + ty + i * kRowGap < H) m |= 1u << i;
-        return m;
-    };
     // tile-major weights: tile t holds [P][32][32]; pixels outside the image are never stored,
     // so whatever sits in their slots is loaded but unused
-    auto weight_ptr = [&](int t) -> const float* {
-        return wts + (size_t)t * (P * kTile * kTile) + ty * kTile + tx;
+    auto weight_ptr = [&](int t) -> const float4* {
+        return reinterpret_cast<const float4*>(wts) + (size_t)t * (P / 4 * kTile * kTile) + ty * kTile + tx;
     };
 
-    TileCoord tc = tile_coord(blockIdx.x, tiles_x, tiles_per_img);
-    unsigned valid = (n_my > 0) ? valid_mask(tc) : 0u;
-    if (n_my > 0) {  // first tile: plain weight fetch
-        const float* wp = weight_ptr(blockIdx.x);
+    int k = 0, c = s0;
+    unsigned valid = 0u;
+    float* o = out.ptr;
+    auto enter_tile = [&](int kk) {  // per-tile state: store pointer and validity of the four pixels
+        const TileCoord tc = tile_coord(blockIdx.x + kk * gridDim.x, tiles_x, tiles_per_img);
+        const int x = tc.x0 + tx;
+        valid = 0u;
 #pragma unroll
-        for (int p = 0; p < P; ++p)
+        for (int i = 0; i < kPx; ++i)
+            if (x < W && tc.y0 + ty + i * kRowGap < H) valid |= 1u << i;
+        o = out.ptr + (long long)tc.b * C * out.plane + (long long)(tc.y0 + ty) * out.pitch + x;
+    };
+    // Pull the weights of the tile after tile ordinal kk (196 KB, contiguous) into L2 while tile kk
+    // is being processed, so that the on-the-fly refill hits L2 instead of HBM.
+    auto prefetch_next_weights = [&](int kk) {
+        int nn = kk + 1;
+        if (nn == n_my) nn = 0;
+        if (nn == kk) return;
+        const float* base = wts + (size_t)(blockIdx.x + nn * gridDim.x) * (P * kTile * kTile);
+        constexpr int kChunk = P * kTile * kTile * 4 / 8;  // 8 chunks, issued by 8 different warps
+        if (lane == 0) bulk_prefetch_l2(reinterpret_cast<const char*>(base) + (size_t)wrp * kChunk, kChunk);
+    };
+    if (total > 0) {  // first tile: plain weight fetch
+        enter_tile(0);
+        prefetch_next_weights(0);
+        const float4* wp = weight_ptr(blockIdx.x);
 #pragma unroll
-            for (int i = 0; i < kPx; ++i) w[i][p] = __ldg(wp + p * (kTile * kTile) + i * kRowGap * kTile);
+        for (int g = 0; g < P / 4; ++g)
+#pragma unroll
+            for (int i = 0; i < kPx; ++i) {
+                const float4 v = __ldg(wp + g * (kTile * kTile) + i * kRowGap * kTile);
+                w[i][4 * g + 0] = v.x;
+                w[i][4 * g + 1] = v.y;
+                w[i][4 * g + 2] = v.z;
+                w[i][4 * g + 3] = v.w;
+            }
     }
 
-    for (int k = 0; k < n_my; ++k) {
-        const bool has_next = (k + 1 < n_my);
-        TileCoord ntc = tc;
-        unsigned nvalid = 0u;
-        const float* nwp = wts;
-        if (has_next) {
-            ntc = tile_coord(blockIdx.x + (k + 1) * gridDim.x, tiles_x, tiles_per_img);
-            nvalid = valid_mask(ntc);
-            nwp = weight_ptr(blockIdx.x + (k + 1) * gridDim.x);
-        }
-        float* o = out.ptr + (long long)tc.b * C * out.plane + (long long)(tc.y0 + ty) * out.pitch + (tc.x0 + tx);
+    for (int item = 0; item < total; ++item) {
+        if (tid == 0 && p_item < total) issue_next();  // refills the stage released by item-1
 
-        for (int c = 0; c < C; ++c, ++item) {
-            if (tid == 0 && p_item < total) issue_next();  // refills the stage released by item-1
+        const int s = item % kStages;
+        const float* sp = stage0 + (size_t)s * (kBox * kBox) + sbase;
+        int nk = k + 1;
+        if (nk == n_my) nk = 0;
+        // last class of this tile visit and another tile follows: refill the weights on the fly
+        const bool reload = (c == C - 1) && (item + 1 < total) && (nk != k);
+        mbar_wait(&full[s], (uint32_t)((item / kStages) & 1));
 
-            const int s = item % kStages;
-            const float* sp = stage0 + (size_t)s * (kBox * kBox) + sbase;
-            mbar_wait(&full[s], (uint32_t)((item / kStages) & 1));
-
-            if (c == C - 1 && has_next)
-                sweep_class<D, DS, true>(w, sp, dil, nwp, acc);
-            else
-                sweep_class<D, DS, false>(w, sp, dil, nwp, acc);
+        if (reload)
+            sweep_class<D, DS, true>(w, sp, dil, weight_ptr(blockIdx.x + nk * gridDim.x), acc);
+        else
+            sweep_class<D, DS, false>(w, sp, dil, nullptr, acc);
 
 #pragma unroll
-            for (int i = 0; i < kPx; ++i)
-                if ((valid >> i) & 1u) o[(long long)c * out.plane + (long long)(i * kRowGap) * out.pitch] = acc[i];
+        for (int i = 0; i < kPx; ++i)
+            if ((valid >> i) & 1u) o[(long long)c * out.plane + (long long)(i * kRowGap) * out.pitch] = acc[i];
 
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);  // this warp no longer reads the stage
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);  // this warp no longer reads the stage
+
+        if (++c == C) {
+            c = 0;
+            if (nk != k) {
+                k = nk;
+                enter_tile(k);
+                prefetch_next_weights(k);
+            }
         }
-        tc = ntc;
-        valid = nvalid;
     }
 }
 
