@@ -38,8 +38,11 @@ __global__ void resize_bilinear_ac_kernel(const float* __restrict__ in, float* _
 // ---------------------------------------------------------------------------------------------
 // affinity weights: one thread per pixel.  K image channels are looped (K = 3 in the trainer).
 // ---------------------------------------------------------------------------------------------
+#ifndef CL4_WEIGHTS_MINBLOCKS
+#define CL4_WEIGHTS_MINBLOCKS 2
+#endif
 template <int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, CL4_WEIGHTS_MINBLOCKS)
 pamr_weights_kernel(const float* __restrict__ img, float* __restrict__ wts, int K, int H, int W, Dilations dil,
                     int tiled) {
     constexpr int P = 8 * D;
@@ -53,11 +56,15 @@ pamr_weights_kernel(const float* __restrict__ img, float* __restrict__ wts, int 
 #pragma unroll
     for (int p = 0; p < P; ++p) logit[p] = 0.f;
 
+#pragma unroll 1
     for (int k = 0; k < K; ++k) {
         const float* pl = img + ((size_t)b * K + k) * HW;
         const float c = __ldg(pl + (size_t)y * W + x);
-        float nb[P];
-        float sum = (float)D * c;  // LocalStDev samples the centre once per dilation (wss/modules.py:92-102)
+        // dlt[p] = neighbour - centre.  The std is taken over the 9*D samples of LocalStDev
+        // (wss/modules.py:86-112): the 8*D neighbours plus the centre once per dilation.  Working
+        // on deviations from the centre keeps the one-pass variance accurate (the D centre
+        // samples contribute zeros).
+        float dlt[P];
 #pragma unroll
         for (int di = 0; di < D; ++di) {
             const int d = dil.d[di];
@@ -66,52 +73,53 @@ pamr_weights_kernel(const float* __restrict__ img, float* __restrict__ wts, int 
             const float* r0 = pl + (size_t)ym * W;
             const float* r1 = pl + (size_t)y * W;
             const float* r2 = pl + (size_t)yp * W;
-            nb[di * 8 + 0] = __ldg(r0 + xm); nb[di * 8 + 1] = __ldg(r0 + x); nb[di * 8 + 2] = __ldg(r0 + xp);
-            nb[di * 8 + 3] = __ldg(r1 + xm);                                  nb[di * 8 + 4] = __ldg(r1 + xp);
-            nb[di * 8 + 5] = __ldg(r2 + xm); nb[di * 8 + 6] = __ldg(r2 + x); nb[di * 8 + 7] = __ldg(r2 + xp);
+            dlt[di * 8 + 0] = __ldg(r0 + xm) - c; dlt[di * 8 + 1] = __ldg(r0 + x) - c; dlt[di * 8 + 2] = __ldg(r0 + xp) - c;
+            dlt[di * 8 + 3] = __ldg(r1 + xm) - c;                                       dlt[di * 8 + 4] = __ldg(r1 + xp) - c;
+            dlt[di * 8 + 5] = __ldg(r2 + xm) - c; dlt[di * 8 + 6] = __ldg(r2 + x) - c; dlt[di * 8 + 7] = __ldg(r2 + xp) - c;
         }
+        float s1 = 0.f;
 #pragma unroll
-        for (int p = 0; p < P; ++p) sum += nb[p];
-        const float mean = sum * (1.f / (float)(9 * D));
-        // two-pass unbiased variance over the 9*D samples
-        float ss = (float)D * (c - mean) * (c - mean);
+        for (int p = 0; p < P; ++p) s1 += dlt[p];
+        const float mean = s1 * (1.f / (float)(9 * D));  // mean deviation over all 9*D samples
+        // two-pass unbiased variance; the D centre samples have deviation 0
+        float ss = (float)D * mean * mean;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            const float t = nb[p] - mean;
+            const float t = dlt[p] - mean;
             ss = fmaf(t, t, ss);
         }
-        const float sd = sqrtf(ss / (float)(9 * D - 1));
-        const float den = 1e-8f + 0.1f * sd;
+        const float sd = sqrtf(ss * (1.f / (float)(9 * D - 1)));
+        const float ninv = -1.f / (1e-8f + 0.1f * sd);  // -1 / (1e-8 + 0.1*std)   (wss/modules.py:143)
 #pragma unroll
-        for (int p = 0; p < P; ++p) logit[p] += __fdiv_rn(-fabsf(c - nb[p]), den);
+        for (int p = 0; p < P; ++p) logit[p] = fmaf(fabsf(dlt[p]), ninv, logit[p]);
     }
-    float mx = -INFINITY;
+    // mean over the K channels (:144), softmax over the 8*D taps (:145)
     const float invK = 1.f / (float)K;
+    float mx = -INFINITY;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        logit[p] = (K == 3) ? __fdiv_rn(logit[p], 3.f) : logit[p] * invK;
+        logit[p] *= invK;
         mx = fmaxf(mx, logit[p]);
     }
     float z = 0.f;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        logit[p] = expf(logit[p] - mx);
+        logit[p] = __expf(logit[p] - mx);
         z += logit[p];
     }
+    const float rz = 1.f / z;
     // planar [B,P,H,W] (public layout) or tile-major [tile][P/4][32][32][4] (what the TMA sweep reads)
-    const float rz = 1.f;
-    (void)rz;
     if (tiled) {
         const size_t tile = ((size_t)b * (gridDim.y / 4) + (y >> 5)) * gridDim.x + blockIdx.x;
         float4* o = reinterpret_cast<float4*>(wts) + tile * ((size_t)(P / 4) * 1024) + (y & 31) * 32 + threadIdx.x;
 #pragma unroll
         for (int g = 0; g < P / 4; ++g)
-            o[(size_t)g * 1024] = make_float4(__fdiv_rn(logit[4 * g], z), __fdiv_rn(logit[4 * g + 1], z),
-                                              __fdiv_rn(logit[4 * g + 2], z), __fdiv_rn(logit[4 * g + 3], z));
+            o[(size_t)g * 1024] = make_float4(logit[4 * g] * rz, logit[4 * g + 1] * rz, logit[4 * g + 2] * rz,
+                                              logit[4 * g + 3] * rz);
     } else {
         float* o = wts + (size_t)b * P * HW + (size_t)y * W + x;
 #pragma unroll
-        for (int p = 0; p < P; ++p) o[(size_t)p * HW] = __fdiv_rn(logit[p], z);
+        for (int p = 0; p < P; ++p) o[(size_t)p * HW] = logit[p] * rz;
     }
 }
 
