@@ -329,7 +329,7 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
             rc = launch_sweep_tma(wts, cur, last ? mask_out : nxt, last ? 0 : 1, B, C, H, W, dil, D, s);
             if (rc != CL4_OK) return rc;
             if (!last) {
-                rc = launch_pad_refresh(nxt, planes, H, W, s);
+                rc = launch_pad_frame(nxt, planes, H, W, s);
                 if (rc != CL4_OK) return rc;
                 float* t = cur; cur = nxt; nxt = t;
             }

@@ -3,7 +3,7 @@
 // Layout.  Between sweeps the masks live in HBM as REPLICATE-PADDED planes
 // [B*C][H+48][W+48] (24 = largest dilation): the clamped neighbour of wss/modules.py:57 is then
 // an ordinary in-bounds read, every 80x80 source window is a plain TMA box and the hot loop has
-// no border case.  A small kernel refreshes the 24-pixel frame after each sweep.
+// no border case.  A small kernel rewrites the 24-pixel frame after each sweep.
 //
 // Sweep kernel.  One persistent CTA per SM (256 threads) walks over 32x32-pixel output tiles in
 // image-major order (neighbouring CTAs share halos in L2).  A thread owns four pixels of one
@@ -179,7 +179,7 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
     };
 
     int k = 0, c = s0;
-    unsigned valid = 0u;
+    unsigned valid = 0u;   // bits 0-3: pixel i lies inside the image
     float* o = out.ptr;
     auto enter_tile = [&](int kk) {  // per-tile state: store pointer and validity of the four pixels
         const TileCoord tc = tile_coord(blockIdx.x + kk * gridDim.x, tiles_x, tiles_per_img);
@@ -263,27 +263,31 @@ __global__ void pamr_pad_copy_kernel(const float* __restrict__ src, float* __res
     dst[((size_t)blockIdx.z * Hp + yp) * Wp + xp] = __ldg(src + ((size_t)blockIdx.z * H + y) * W + x);
 }
 
-// In place: frame cells of a padded plane <- nearest interior cell.  One thread per frame cell:
-// the frame is 2*pad full rows (top/bottom) + H rows x 2*pad columns (left/right).
-__global__ void pamr_pad_refresh_kernel(float* __restrict__ buf, int H, int W) {
+// In place: the 24-pixel frame of every padded plane <- nearest image pixel (replicate padding,
+// wss/modules.py:57, for the NEXT sweep).  Only frame cells are written and only image cells are
+// read, so blocks need no ordering.  blockIdx.x < bands_blocks: the 2 x 24 full-width rows above
+// and below the image, one thread per cell; the remaining blocks: one warp per image row writes
+// its 24 + 24 frame columns.
+__global__ void __launch_bounds__(256)
+pamr_pad_frame_kernel(float* __restrict__ buf, int H, int W, int bands_blocks) {
     const int Wp = W + 2 * kHalo, Hp = H + 2 * kHalo;
     float* pl = buf + (size_t)blockIdx.y * Hp * Wp;
-    const int n_rows_part = 2 * kHalo * Wp;  // top and bottom bands
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int yp, xp;
-    if (i < n_rows_part) {
-        const int r = i / Wp;
-        xp = i - r * Wp;
-        yp = (r < kHalo) ? r : (H + r);  // r in [24,48) -> rows H+24 .. H+47
+    if ((int)blockIdx.x < bands_blocks) {
+        const int i = blockIdx.x * 256 + threadIdx.x;
+        if (i >= 2 * kHalo * Wp) return;
+        const int r = i / Wp, xp = i - r * Wp;
+        const int yp = (r < kHalo) ? r : (H + r);              // 0..23 and H+24..H+47
+        const int ys = (r < kHalo) ? kHalo : (H + kHalo - 1);  // first / last image row
+        pl[(size_t)yp * Wp + xp] = pl[(size_t)ys * Wp + clampi(xp, kHalo, W + kHalo - 1)];
     } else {
-        const int j = i - n_rows_part;
-        if (j >= H * 2 * kHalo) return;
-        const int r = j / (2 * kHalo), cidx = j - r * (2 * kHalo);
-        yp = r + kHalo;
-        xp = (cidx < kHalo) ? cidx : (W + cidx);
+        const int row = ((int)blockIdx.x - bands_blocks) * 8 + (threadIdx.x >> 5);
+        const int lane = threadIdx.x & 31;
+        if (row >= H || lane >= kHalo) return;
+        float* rp = pl + (size_t)(row + kHalo) * Wp;
+        const float vl = rp[kHalo], vr = rp[kHalo + W - 1];
+        rp[lane] = vl;
+        rp[kHalo + W + lane] = vr;
     }
-    const int ys = clampi(yp, kHalo, H + kHalo - 1), xs = clampi(xp, kHalo, W + kHalo - 1);
-    pl[(size_t)yp * Wp + xp] = pl[(size_t)ys * Wp + xs];
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -337,11 +341,11 @@ int launch_pad_copy(const float* src, float* dst, long long planes, int H, int W
     return check_launch("pamr_pad_copy");
 }
 
-int launch_pad_refresh(float* buf, long long planes, int H, int W, cudaStream_t s) {
-    const int cells = 2 * kHalo * (W + 2 * kHalo) + H * 2 * kHalo;
-    dim3 grid(ceil_div(cells, 256), (unsigned)planes);
-    pamr_pad_refresh_kernel<<<grid, 256, 0, s>>>(buf, H, W);
-    return check_launch("pamr_pad_refresh");
+int launch_pad_frame(float* buf, long long planes, int H, int W, cudaStream_t s) {
+    const int bands_blocks = ceil_div(2 * kHalo * (W + 2 * kHalo), 256);
+    dim3 grid(bands_blocks + ceil_div(H, 8), (unsigned)planes);
+    pamr_pad_frame_kernel<<<grid, 256, 0, s>>>(buf, H, W, bands_blocks);
+    return check_launch("pamr_pad_frame");
 }
 
 template <int D, class DS>
@@ -376,7 +380,7 @@ static int launch_D(const CUtensorMap& tmap, const float* w, const SweepOut& out
 }
 
 // padded_in: [B*C][H+48][W+48].  out_padded != 0: `out` is a padded buffer of the same shape (its
-// frame is NOT refreshed here); otherwise `out` is the plain [B*C][H][W] tensor.
+// frame is rewritten afterwards by launch_pad_frame); otherwise `out` is the plain [B*C][H][W] tensor.
 int launch_sweep_tma(const float* w, const float* padded_in, float* out, int out_padded, int B, int C, int H, int W,
                      const Dilations& dil, int D, cudaStream_t s) {
     CUtensorMap tmap;

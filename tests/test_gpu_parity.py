@@ -42,6 +42,9 @@ def test_pamr_golden(cl4, golden, name):
 @pytest.mark.parametrize("B,C,H,W,dil,T", [
     (2, 21, 96, 80, [1, 2, 4, 8, 12, 24], 10),
     (1, 7, 33, 65, [1, 2, 4, 8, 12], 10),
+    (2, 3, 50, 72, [1, 2, 4, 8, 12, 24], 10),    # partial tiles in both dimensions on the TMA path
+    (1, 2, 32, 36, [1, 2, 4, 8, 12, 24], 3),     # one tile row: top and bottom frame from the same tile
+    (1, 2, 200, 32, [1, 24], 5),
     (3, 2, 17, 130, [1, 2, 4, 8, 12, 24], 4),
     (1, 1, 5, 3, [1, 2, 4, 8, 12, 24], 10),      # every dilation exceeds the image
     (2, 3, 32, 32, [1, 2, 4, 8, 12], 10),        # the trainer's feature-resolution regime
