@@ -277,6 +277,10 @@ def main():
                "d2h_bytes_per_step": pipe.d2h_bytes, "timing": "wall clock around K pipelined steps, sync on both sides"}
         del pipe
 
+    # leave the process group cleanly before anything is printed (NCCL warns on stderr otherwise)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        cdist.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
 
