@@ -259,7 +259,7 @@ def main():
     # ---- end to end through host buffers (pinned H2D of inputs + D2H of results every step)
     e2e = None
     if not args.no_e2e:
-        pipe = cl4.HostPseudoLabelPipeline(B, C, H, W, n_slots=2, num_iter=T, dilations=dil, threshold=cfg["thr"],
+        pipe = cl4.HostPseudoLabelPipeline(B, C, H, W, n_slots=3, num_iter=T, dilations=dil, threshold=cfg["thr"],
                                            nms_kernel=cfg["nms"], max_centers=max(256, 2 * cfg["Kc"]))
         for _ in range(W_):
             pipe.submit(h_img, h_mask, h_heat, h_off)

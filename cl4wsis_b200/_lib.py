@@ -36,6 +36,8 @@ SIGNATURES = {
     "cl4_peak_extract": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _int, _int, _int, _int, _int, _int, _vp]),
     "cl4_center_nms_scratch_bytes": (_sz, [_int] * 3),
     "cl4_center_nms": (_int, [_vp, _flt, _flt, _int, _int, _int, _int, _vp, _vp, _int, _vp, _sz, _vp]),
+    "cl4_ccl4_scratch_bytes": (_sz, [_int, _int]),
+    "cl4_ccl4_components": (_int, [_vp, _vp, _flt, _flt, _flt, _int, _int, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
     "cl4_group_pixels": (_int, [_vp, _vp, _int, _int, _vp, _vp, _vp, _int, _int, _int, _int, _vp]),
 }
 

@@ -344,6 +344,12 @@ static int launch_peak(const float* heat, float* scores, int* ys, int* xs, unsig
     return check_launch("peak_merge");
 }
 
+int launch_center_compact(const uint32_t* words, int N, int H, int words_per_row, long long* ctr_out, int* count_out,
+                          int max_out, int* row_off, cudaStream_t s) {
+    center_compact_kernel<<<N, 1024, 0, s>>>(words, H, words_per_row, ctr_out, count_out, max_out, row_off);
+    return check_launch("center_compact");
+}
+
 }  // namespace cl4
 
 extern "C" size_t cl4_center_nms_scratch_bytes(int N, int H, int W) {
@@ -377,8 +383,7 @@ extern "C" int cl4_center_nms(const float* heat, float threshold, float min_valu
     center_flags_kernel<<<grid, kNmsThreads, smem, s>>>(heat, threshold, min_value, r, H, W, wpr, words);
     int rc = check_launch("center_flags");
     if (rc != CL4_OK) return rc;
-    center_compact_kernel<<<N, 1024, 0, s>>>(words, H, wpr, ctr_out, count_out, max_out, row_off);
-    return check_launch("center_compact");
+    return launch_center_compact(words, N, H, wpr, ctr_out, count_out, max_out, row_off, s);
 }
 
 extern "C" size_t cl4_peak_extract_scratch_bytes(int B, int C, int H, int W, int kernel, int K) {

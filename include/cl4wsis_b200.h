@@ -121,6 +121,23 @@ int cl4_group_pixels(const long long* ctr, const int* count_dev, int Kc, int ctr
                      const unsigned char* fg, long long* ids, int N, int H, int W, int empty_mode,
                      cl4_stream_t stream);
 
+/* ------------------------------------------------------------------------- *
+ * Connected components for cluster_peaks — modules/utils.py:608-632 (the centre
+ * clustering of get_instance_segmentation, :567-594).
+ *   weak = (sqrt(off_x^2 + off_y^2) < thresh) & fg
+ *   cv2.connectedComponentsWithStats(weak, connectivity=4); keep area_lo < area < area_hi
+ * offsets [2,H,W] fp32 (dy,dx), fg [H,W] uint8.  roots_out [max_out,2] int64: first
+ * pixel (y,x) of every kept component in OpenCV's label order (raster order of the
+ * first pixel); stats_out [max_out+1,3] int64: row 0 = OpenCV's label 0 (all other
+ * pixels): area, sum x, sum y; rows 1.. = the kept components; count_out [1] int32 =
+ * number of kept components (may exceed max_out).  centroid = sum / area in double,
+ * exactly OpenCV's.
+ * ------------------------------------------------------------------------- */
+size_t cl4_ccl4_scratch_bytes(int H, int W);
+int cl4_ccl4_components(const float* offsets, const unsigned char* fg, float thresh, float area_lo, float area_hi,
+                        int H, int W, long long* roots_out, long long* stats_out, int* count_out, int max_out,
+                        void* scratch, size_t scratch_bytes, cl4_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -173,12 +173,43 @@ def group_pixels(ctr, offsets, fg=None):
     return ids
 
 
+def cluster_peaks(offset_map, fg, thresh=2.5, beta=5):
+    """modules/utils.py:608-632: 4-connected components (OpenCV, as the reference) of the weak-offset
+    foreground; centroids (y,x) of the components with 21-beta < area < 21+beta, label 0 included."""
+    import cv2
+    off = _f32(offset_map)
+    mag = np.sqrt(off[1] * off[1] + off[0] * off[0])
+    weak = ((mag < thresh) & (np.asarray(fg) != 0)).astype(np.uint8)
+    n, _, stats, cent = cv2.connectedComponentsWithStats(weak, connectivity=4)
+    return np.int32([cent[k][::-1] for k in range(n) if 21 - beta < stats[k, cv2.CC_STAT_AREA] < 21 + beta])
+
+
 def get_instance_segmentation(fg, ctr_hmp, offsets, threshold=0.1, nms_kernel=3, top_k=None, ignore=True, beta=0):
-    """beta <= 0 path of modules/utils.py:545-606 (no centre clustering)."""
-    if beta > 0:
-        raise NotImplementedError("oracle covers the beta<=0 path; cluster_peaks is a 'next' row (SURVEY §8f)")
-    ctr = find_instance_center(ctr_hmp, threshold, nms_kernel, top_k)
+    """modules/utils.py:545-606.  Returns (ids, heat_after): the reference marks accepted cluster
+    centres with 1.0 in ctr_hmp in place; the oracle returns the marked copy instead."""
+    ctr_hmp = _f32(ctr_hmp).copy()
+    offsets = _f32(offsets)
     fg = np.asarray(fg)
-    if ctr.shape[0] == 0:
-        return np.zeros(fg.shape, np.int64) if ignore else fg.astype(np.int64)
-    return group_pixels(ctr, offsets, fg=fg)
+    ctr = find_instance_center(ctr_hmp, threshold, nms_kernel, top_k)
+    new_ctr = ctr
+    if beta > 0:
+        cl = cluster_peaks(offsets[0], fg[0], beta=beta)
+        cl = np.array([[cy, cx] for cy, cx in cl if ctr_hmp[0, 0, cy, cx] > 0.05], dtype=np.int64).reshape(-1, 2)
+        if len(cl):
+            if len(ctr) == 0:
+                new_ctr = cl
+                ctr_hmp[0, 0, cl[:, 0], cl[:, 1]] = 1.0
+            else:
+                keep = []
+                for c in cl:
+                    d = np.sqrt(((ctr.astype(np.float32) - c.astype(np.float32)) ** 2).sum(-1, dtype=np.float32)).min()
+                    if d > 100:
+                        keep.append(c)
+                        ctr_hmp[0, 0, c[0], c[1]] = 1.0
+                if keep:
+                    new_ctr = np.concatenate([ctr, np.array(keep, np.int64)], 0)
+    if new_ctr.shape[0] == 0:
+        ids = np.zeros(fg.shape, np.int64) if ignore else fg.astype(np.int64)
+    else:
+        ids = group_pixels(new_ctr, offsets, fg=fg)
+    return ids, ctr_hmp

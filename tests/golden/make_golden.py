@@ -211,6 +211,40 @@ def main():
         out[f"inst_{g}__args"] = np.array([thr, k, float(ignore), beta], np.float64)
         out[f"inst_{g}__ids"] = ids
         g += 1
+    # centre clustering exercised for real (modules/utils.py:567-594): exact offsets give a 21-pixel
+    # weak-offset disk around every planted centre; heat peaks exist only for some of them
+    def cluster_case(H, W, centres, peaks, base, thr, k, beta, fg_holes):
+        yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+        cs = np.array(centres, np.int64)
+        off = offsets_to(rng, H, W, cs, 0.0)[None]
+        heat = np.full((H, W), base, np.float32)
+        for (cy, cx, a) in peaks:
+            heat = np.maximum(heat, a * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / 72.0).astype(np.float32))
+        fg = np.ones((1, H, W), bool)
+        for (y0, y1, x0, x1) in fg_holes:
+            fg[0, y0:y1, x0:x1] = False
+        return fg, heat[None, None], off, thr, k, True, beta
+
+    extra = [
+        # two NMS centres + two far cluster centres (one added, one within 100 px of an NMS centre)
+        cluster_case(200, 260, [(30, 40), (40, 230), (170, 60), (60, 90)], [(30, 40, 0.9), (40, 230, 0.8)], 0.06, 0.3, 41, 3.0, []),
+        # no NMS centre at all: the cluster centres become the centres
+        cluster_case(120, 150, [(20, 30), (90, 120)], [], 0.1, 0.3, 41, 5, []),
+        # cluster centre heat below 0.05 is ignored; a hole in fg splits a disk
+        cluster_case(180, 180, [(30, 30), (150, 150)], [(30, 30, 0.9)], 0.01, 0.3, 5, 5, [(148, 153, 150, 151)]),
+        # beta too small for the 21-pixel disks to pass (21-1 < area < 21+1 still passes 21)
+        cluster_case(160, 200, [(25, 25), (140, 170)], [(25, 25, 0.7)], 0.2, 0.3, 41, 1, []),
+    ]
+    for (fg, hm0, off, thr, k, ignore, beta) in extra:
+        hm = hm0.copy()
+        ids = mu.get_instance_segmentation(torch.from_numpy(fg), torch.from_numpy(hm), torch.from_numpy(off),
+                                           threshold=thr, nms_kernel=k, top_k=None, ignore=ignore, beta=beta).numpy()
+        out[f"inst_{g}__fg"], out[f"inst_{g}__heat"], out[f"inst_{g}__off"] = fg, hm0, off
+        out[f"inst_{g}__heat_after"] = hm
+        out[f"inst_{g}__args"] = np.array([thr, k, float(ignore), beta], np.float64)
+        out[f"inst_{g}__ids"] = ids
+        print("cluster case", g, "ids max", int(ids.max()), "cells marked", int((hm != hm0).sum()))
+        g += 1
     out["inst__n"] = np.array(g, np.int32)
 
     path = os.path.join(HERE, "reference_golden.npz")

@@ -245,20 +245,36 @@ def test_group_pixels_errors(cl4):
 
 
 # --------------------------------------------------------------------------- get_instance_segmentation
-def test_get_instance_segmentation_golden_beta0(cl4, golden):
-    seen = 0
-    for i in range(int(golden["inst__n"])):
+def test_get_instance_segmentation_golden(cl4, golden):
+    """Every fixture case, with and without centre clustering; the in-place marking of merged cluster
+    centres in ctr_hmp (modules/utils.py:583,591) is part of the contract."""
+    n, seen_beta = int(golden["inst__n"]), 0
+    for i in range(n):
         thr, k, ignore, beta = golden[f"inst_{i}__args"]
-        if beta > 0:
-            continue
         hm = cuda(golden[f"inst_{i}__heat"])
         got = cl4.get_instance_segmentation(cuda(golden[f"inst_{i}__fg"]), hm, cuda(golden[f"inst_{i}__off"]),
                                             threshold=float(thr), nms_kernel=int(k), top_k=None, ignore=bool(ignore),
-                                            beta=0)
+                                            beta=beta)
         assert got.dtype == torch.int64
         assert np.array_equal(got.cpu().numpy(), golden[f"inst_{i}__ids"]), i
-        seen += 1
-    assert seen >= 3
+        assert np.array_equal(hm.cpu().numpy(), golden[f"inst_{i}__heat_after"]), i
+        seen_beta += beta > 0
+    assert n >= 9 and seen_beta >= 6
+
+
+@pytest.mark.parametrize("H,W,p,beta", [(64, 80, 0.5, 5), (200, 333, 0.3, 3.0), (37, 41, 0.7, 20), (512, 512, 0.45, 5),
+                                        (16, 16, 0.97, 21)])
+def test_cluster_peaks_matches_opencv(cl4, oracle, H, W, p, beta):
+    """GPU connected components vs the reference's cv2 path: same components, same order, same
+    truncated centroids — including OpenCV's label 0 (the complement) when its area passes the filter."""
+    from cl4wsis_b200.cluster import cluster_peaks
+    rng = np.random.default_rng(H * W)
+    off = (rng.standard_normal((1, 2, H, W)) * (2.5 / np.sqrt(-2 * np.log(1 - p + 1e-9)))).astype(np.float32)
+    fg = rng.random((1, H, W)) > 0.1
+    want = oracle.cluster_peaks(off[0], fg[0], beta=beta)
+    got = cluster_peaks(cuda(off), cuda(fg), beta=beta)
+    assert got.dtype == np.int32 and got.shape == want.reshape(-1, 2).shape
+    assert np.array_equal(got, want.reshape(-1, 2))
 
 
 # --------------------------------------------------------------------------- batched step

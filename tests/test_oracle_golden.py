@@ -96,15 +96,16 @@ def test_group_pixels_matches_reference(golden, oracle):
     assert ids[0, 1].tolist() == [1, 1, 1, 1, 2, 2, 2, 2]
 
 
-def test_get_instance_segmentation_beta0_matches_reference(golden, oracle):
+def test_get_instance_segmentation_matches_reference(golden, oracle):
+    """All fixture cases, with and without centre clustering (beta > 0 uses OpenCV like the reference)."""
     n = int(golden["inst__n"])
-    seen = 0
+    seen_beta = 0
     for i in range(n):
         thr, k, ignore, beta = golden[f"inst_{i}__args"]
-        if beta > 0:
-            continue
-        got = oracle.get_instance_segmentation(golden[f"inst_{i}__fg"], golden[f"inst_{i}__heat"],
-                                               golden[f"inst_{i}__off"], float(thr), int(k), None, bool(ignore), 0)
+        got, heat_after = oracle.get_instance_segmentation(golden[f"inst_{i}__fg"], golden[f"inst_{i}__heat"],
+                                                           golden[f"inst_{i}__off"], float(thr), int(k), None,
+                                                           bool(ignore), beta)
         assert np.array_equal(got, golden[f"inst_{i}__ids"]), i
-        seen += 1
-    assert seen >= 3
+        assert np.array_equal(heat_after, golden[f"inst_{i}__heat_after"]), i
+        seen_beta += beta > 0
+    assert n >= 5 and seen_beta >= 2
