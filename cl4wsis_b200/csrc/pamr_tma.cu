@@ -9,8 +9,9 @@
 // image-major order (neighbouring CTAs share halos in L2).  A thread owns four pixels of one
 // column, 4 rows apart, and keeps their 4 x 8D affinity weights in registers for all C classes
 // of the tile (the weights are the only per-pixel state; 192 registers at D = 6).  Per class the
-// 80x80 window arrives by ONE cp.async.bulk.tensor box load into a 6-stage shared-memory ring
-// guarded by full/empty mbarriers, so the copies of the next five classes overlap the FMAs.
+// 80x80 window arrives by ONE cp.async.bulk.tensor box load into a 4-stage shared-memory ring
+// guarded by full/empty mbarriers, so the copies of the next three classes overlap the FMAs
+// (3 to 6 stages measure the same; 8 is slower because the L1 left for the weight refill shrinks).
 // The inner loop is LDS (immediate offset) + FFMA; because the four pixels sit 4 rows apart,
 // 39 of their 192 (pixel, tap) sources coincide and are loaded once (153 LDS per 192 FFMA) —
 // the loop is bound by shared-memory bandwidth (one 128-byte wavefront per cycle), not by FP32.
@@ -27,7 +28,14 @@ namespace cl4 {
 constexpr int kTile = 32;
 constexpr int kHalo = kPamrPad;                 // 24: largest supported dilation on this path
 constexpr int kBox = kTile + 2 * kHalo;         // 80
-constexpr int kStages = 6;
+#ifndef CL4_SWEEP_STAGES
+#define CL4_SWEEP_STAGES 4
+#endif
+#ifndef CL4_SWEEP_PRODUCER
+#define CL4_SWEEP_PRODUCER 0
+#endif
+constexpr int kStages = CL4_SWEEP_STAGES;
+constexpr int kProducerTid = CL4_SWEEP_PRODUCER;  // the thread that issues the TMA loads
 constexpr int kSweepThreads = 256;              // 8 warps; warp (h,q) owns rows h*16 + q + 4*i, i = 0..3
 constexpr int kPx = 4;                          // pixels per thread
 constexpr int kRowGap = 4;
@@ -164,7 +172,7 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
         tma_load_3d(stage0 + (size_t)s * (kBox * kBox), &tmap, &full[s], ptc.x0, ptc.y0, ptc.b * C + pc);
         ++p_item;
     };
-    if (tid == 0) {
+    if (tid == kProducerTid) {
         for (int i = 0; i < kStages - 1 && p_item < total; ++i) issue_next();
     }
 
@@ -217,7 +225,7 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
     }
 
     for (int item = 0; item < total; ++item) {
-        if (tid == 0 && p_item < total) issue_next();  // refills the stage released by item-1
+        if (tid == kProducerTid && p_item < total) issue_next();  // refills the stage released by item-1
 
         const int s = item % kStages;
         const float* sp = stage0 + (size_t)s * (kBox * kBox) + sbase;
@@ -253,40 +261,65 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
 // ---------------------------------------------------------------------------------------------
 // Replicate-padded planes.
 // ---------------------------------------------------------------------------------------------
-// dst [planes][H+2*pad][W+2*pad] <- replicate-pad(src [planes][H][W])
-__global__ void pamr_pad_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W) {
-    const int Wp = W + 2 * kHalo, Hp = H + 2 * kHalo;
-    const int xp = blockIdx.x * blockDim.x + threadIdx.x;
-    const int yp = blockIdx.y * blockDim.y + threadIdx.y;
-    if (xp >= Wp || yp >= Hp) return;
-    const int y = clampi(yp - kHalo, 0, H - 1), x = clampi(xp - kHalo, 0, W - 1);
-    dst[((size_t)blockIdx.z * Hp + yp) * Wp + xp] = __ldg(src + ((size_t)blockIdx.z * H + y) * W + x);
+// dst [planes][H+2*pad][W+2*pad] <- replicate-pad(src [planes][H][W]).  One thread per float4 of a
+// padded row (W % 4 == 0 on this path, so image columns map to aligned float4 loads).
+__global__ void __launch_bounds__(256)
+pamr_pad_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W) {
+    const int Wp = W + 2 * kHalo, Hp = H + 2 * kHalo, w4 = Wp / 4;
+    const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yp = blockIdx.y;
+    if (x4 >= w4) return;
+    const int y = clampi(yp - kHalo, 0, H - 1);
+    const float* srow = src + ((size_t)blockIdx.z * H + y) * W;
+    const int x = x4 * 4 - kHalo;  // image column of the first element
+    float4 v;
+    if (x >= 0 && x + 3 < W) {
+        v = __ldg(reinterpret_cast<const float4*>(srow + x));
+    } else {
+        v.x = __ldg(srow + clampi(x, 0, W - 1));
+        v.y = __ldg(srow + clampi(x + 1, 0, W - 1));
+        v.z = __ldg(srow + clampi(x + 2, 0, W - 1));
+        v.w = __ldg(srow + clampi(x + 3, 0, W - 1));
+    }
+    reinterpret_cast<float4*>(dst + ((size_t)blockIdx.z * Hp + yp) * Wp)[x4] = v;
 }
 
 // In place: the 24-pixel frame of every padded plane <- nearest image pixel (replicate padding,
 // wss/modules.py:57, for the NEXT sweep).  Only frame cells are written and only image cells are
 // read, so blocks need no ordering.  blockIdx.x < bands_blocks: the 2 x 24 full-width rows above
-// and below the image, one thread per cell; the remaining blocks: one warp per image row writes
-// its 24 + 24 frame columns.
+// and below the image, one thread per float4; the remaining blocks: one thread per image row
+// writes its 24 + 24 frame columns as 6 + 6 float4.
 __global__ void __launch_bounds__(256)
 pamr_pad_frame_kernel(float* __restrict__ buf, int H, int W, int bands_blocks) {
-    const int Wp = W + 2 * kHalo, Hp = H + 2 * kHalo;
+    const int Wp = W + 2 * kHalo, Hp = H + 2 * kHalo, w4 = Wp / 4;
     float* pl = buf + (size_t)blockIdx.y * Hp * Wp;
     if ((int)blockIdx.x < bands_blocks) {
         const int i = blockIdx.x * 256 + threadIdx.x;
-        if (i >= 2 * kHalo * Wp) return;
-        const int r = i / Wp, xp = i - r * Wp;
+        if (i >= 2 * kHalo * w4) return;
+        const int r = i / w4, x4 = i - r * w4;
         const int yp = (r < kHalo) ? r : (H + r);              // 0..23 and H+24..H+47
         const int ys = (r < kHalo) ? kHalo : (H + kHalo - 1);  // first / last image row
-        pl[(size_t)yp * Wp + xp] = pl[(size_t)ys * Wp + clampi(xp, kHalo, W + kHalo - 1)];
+        const float* srow = pl + (size_t)ys * Wp;
+        const int xp = x4 * 4;
+        float4 v;
+        if (xp >= kHalo && xp + 3 < W + kHalo) {
+            v = *reinterpret_cast<const float4*>(srow + xp);
+        } else {
+            const float e = (xp < kHalo) ? srow[kHalo] : srow[W + kHalo - 1];
+            v = make_float4(e, e, e, e);  // a frame float4 never straddles the image (24 % 4 == 0)
+        }
+        reinterpret_cast<float4*>(pl + (size_t)yp * Wp)[x4] = v;
     } else {
-        const int row = ((int)blockIdx.x - bands_blocks) * 8 + (threadIdx.x >> 5);
-        const int lane = threadIdx.x & 31;
-        if (row >= H || lane >= kHalo) return;
+        const int row = ((int)blockIdx.x - bands_blocks) * 256 + threadIdx.x;
+        if (row >= H) return;
         float* rp = pl + (size_t)(row + kHalo) * Wp;
         const float vl = rp[kHalo], vr = rp[kHalo + W - 1];
-        rp[lane] = vl;
-        rp[kHalo + W + lane] = vr;
+        const float4 l4 = make_float4(vl, vl, vl, vl), r4 = make_float4(vr, vr, vr, vr);
+#pragma unroll
+        for (int q = 0; q < kHalo / 4; ++q) {
+            reinterpret_cast<float4*>(rp)[q] = l4;
+            reinterpret_cast<float4*>(rp + kHalo + W)[q] = r4;
+        }
     }
 }
 
@@ -336,14 +369,14 @@ size_t tiled_weight_elems(int B, int H, int W, int D) {
 size_t padded_plane_elems(int H, int W) { return (size_t)(H + 2 * kHalo) * (size_t)(W + 2 * kHalo); }
 
 int launch_pad_copy(const float* src, float* dst, long long planes, int H, int W, cudaStream_t s) {
-    dim3 block(32, 8), grid(ceil_div(W + 2 * kHalo, 32), ceil_div(H + 2 * kHalo, 8), (unsigned)planes);
-    pamr_pad_copy_kernel<<<grid, block, 0, s>>>(src, dst, H, W);
+    dim3 grid(ceil_div((W + 2 * kHalo) / 4, 256), H + 2 * kHalo, (unsigned)planes);
+    pamr_pad_copy_kernel<<<grid, 256, 0, s>>>(src, dst, H, W);
     return check_launch("pamr_pad_copy");
 }
 
 int launch_pad_frame(float* buf, long long planes, int H, int W, cudaStream_t s) {
-    const int bands_blocks = ceil_div(2 * kHalo * (W + 2 * kHalo), 256);
-    dim3 grid(bands_blocks + ceil_div(H, 8), (unsigned)planes);
+    const int bands_blocks = ceil_div(2 * kHalo * ((W + 2 * kHalo) / 4), 256);
+    dim3 grid(bands_blocks + ceil_div(H, 256), (unsigned)planes);
     pamr_pad_frame_kernel<<<grid, 256, 0, s>>>(buf, H, W, bands_blocks);
     return check_launch("pamr_pad_frame");
 }
