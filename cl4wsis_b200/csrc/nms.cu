@@ -62,6 +62,134 @@ __device__ __forceinline__ float row_window_max(const float* s_col, int pitch, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fast path for the NMS kernels the reference actually uses (k = 3, 5, 15, 41; R = (k-1)/2 at
+// compile time).  Values are mapped to order-preserving int32 keys (NaN -> INT_MAX, so an integer
+// max IS ATen's NaN-propagating max; -0.0 folded onto +0.0 so key equality IS float equality) and
+// the k-wide running maximum is taken in registers by doubling (max over 1,2,4,.. wide windows),
+// first down the columns, then along the rows with 128-bit shared-memory loads.
+// ---------------------------------------------------------------------------------------------
+constexpr int kKeyNaN = 0x7fffffff;
+constexpr int kKeyPad = (int)0x80000000;  // below every real key: ATen's implicit -inf padding
+
+__device__ __forceinline__ int float_key(float v) {
+    if (v != v) return kKeyNaN;
+    int b = __float_as_int(v);
+    b ^= (b >> 31) & 0x7fffffff;
+    return (b == -1) ? 0 : b;  // -0.0 -> +0.0
+}
+__device__ __forceinline__ float key_float(int k) {  // inverse (NaN and -0.0 are not restored exactly)
+    k ^= (k >> 31) & 0x7fffffff;
+    return __int_as_float(k);
+}
+
+template <int N, int K, int Wd>
+__device__ __forceinline__ void window_max_level(int (&m)[N]) {
+    if constexpr (2 * Wd <= K) {
+#pragma unroll
+        for (int i = 0; i + Wd < N; ++i) m[i] = max(m[i], m[i + Wd]);
+        window_max_level<N, K, 2 * Wd>(m);
+    } else if constexpr (Wd < K) {
+#pragma unroll
+        for (int i = 0; i + K - Wd < N; ++i) m[i] = max(m[i], m[i + K - Wd]);
+    }
+}
+// in place: afterwards m[i] = max(m[i .. i+K-1]) for i <= N-K
+template <int N, int K>
+__device__ __forceinline__ void window_max(int (&m)[N]) {
+    window_max_level<N, K, 1>(m);
+}
+
+template <int R>
+struct FastTile {
+    static constexpr int K = 2 * R + 1;
+    static constexpr int kCols = kTileW + 2 * R;              // columns of the staged window
+    static constexpr int kPitch = (kCols + 3) / 4 * 4 + 4;    // multiple of 4 for the 128-bit row loads
+    static constexpr int kRows = kTileH + 2 * R;
+    static constexpr size_t kSmem = sizeof(int) * (size_t)kPitch * (kRows + kTileH);
+    static constexpr int kRun = 8;                            // rows per vertical task
+
+    // s_key: staged keys, s_col: column-wise window maxima for all kCols columns
+    template <bool kThreshold>
+    __device__ static void stage_and_columns(const float* __restrict__ plane, int H, int W, int y0, int x0, float thr,
+                                             int* s_key, int* s_col) {
+        for (int i = threadIdx.x; i < kRows * kCols; i += kNmsThreads) {
+            const int ty = i / kCols, tx = i - ty * kCols;
+            const int y = y0 + ty - R, x = x0 + tx - R;
+            int k = kKeyPad;
+            if (y >= 0 && y < H && x >= 0 && x < W) {
+                float v = __ldg(plane + (size_t)y * W + x);
+                if (kThreshold) v = (v <= thr) ? -1.f : v;  // F.threshold(x, thr, -1)
+                k = float_key(v);
+            }
+            s_key[ty * kPitch + tx] = k;
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < kCols * (kTileH / kRun); q += kNmsThreads) {
+            const int run = q / kCols, col = q - run * kCols;
+            int m[kRun + 2 * R];
+#pragma unroll
+            for (int j = 0; j < kRun + 2 * R; ++j) m[j] = s_key[(run * kRun + j) * kPitch + col];
+            window_max<kRun + 2 * R, K>(m);
+#pragma unroll
+            for (int j = 0; j < kRun; ++j) s_col[(run * kRun + j) * kPitch + col] = m[j];
+        }
+        __syncthreads();
+    }
+
+    // k x k window maxima of the 4 pixels (ty, 4*q4 .. 4*q4+3) of the tile
+    __device__ static void row_max4(const int* s_col, int ty, int q4, int (&out)[4]) {
+        constexpr int N = (4 + 2 * R + 3) / 4 * 4;
+        int m[N];
+        const int4* p = reinterpret_cast<const int4*>(s_col + ty * kPitch + 4 * q4);
+#pragma unroll
+        for (int j = 0; j < N / 4; ++j) {
+            const int4 v = p[j];
+            m[4 * j] = v.x; m[4 * j + 1] = v.y; m[4 * j + 2] = v.z; m[4 * j + 3] = v.w;
+        }
+        window_max<N, K>(m);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] = m[j];
+    }
+};
+
+template <int R>
+__global__ void __launch_bounds__(kNmsThreads)
+center_flags_fast_kernel(const float* __restrict__ heat, float thr, float min_value, int H, int W, int words_per_row,
+                         uint32_t* __restrict__ words) {
+    using T = FastTile<R>;
+    extern __shared__ __align__(16) int smem_i[];
+    int* s_key = smem_i;
+    int* s_col = smem_i + T::kPitch * T::kRows;
+    const int n = blockIdx.z;
+    const int y0 = blockIdx.y * kTileH, x0 = blockIdx.x * kTileW;
+    T::template stage_and_columns<true>(heat + (size_t)n * H * W, H, W, y0, x0, thr, s_key, s_col);
+
+    // thread -> (row, 4-pixel group): lanes 0-15 one row, lanes 16-31 the next; two passes cover 32 rows
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int ty = pass * 16 + warp * 2 + (lane >> 4), q4 = lane & 15;
+        int mx[4];
+        T::row_max4(s_col, ty, q4, mx);
+        unsigned bits = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int kv = s_key[(ty + R) * T::kPitch + R + 4 * q4 + j];
+            const int y = y0 + ty, x = x0 + 4 * q4 + j;
+            const bool keep = (y < H) && (x < W) && (kv == mx[j]) && (kv != kKeyNaN) && (key_float(kv) > min_value);
+            bits |= (keep ? 1u : 0u) << j;
+        }
+        // assemble 32-pixel words: lane l holds pixels 4*(l&15).. of row (l>>4); 8 lanes make a word
+        unsigned word = bits << (4 * (lane & 7));
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) word |= __shfl_xor_sync(0xffffffffu, word, o);
+        const int xw = (x0 >> 5) + ((lane >> 3) & 1);
+        const int y = y0 + ty;
+        if ((lane & 7) == 0 && y < H && xw < words_per_row) words[((size_t)n * H + y) * words_per_row + xw] = word;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Centre NMS, pass 1: one 32-bit keep-mask word per 32 consecutive x.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kNmsThreads)
@@ -234,12 +362,40 @@ struct WarpTopK {
     // offer one candidate per lane (0 = none)
     __device__ __forceinline__ void offer(unsigned long long cand, int lane) {
         uint32_t m = __ballot_sync(0xffffffffu, cand > thresh);
+        if (KPL == 1 && __popc(m) > 3) {  // many newcomers (e.g. the first fill): one sort + merge
+            merge32(cand > thresh ? cand : 0ull, lane);
+            return;
+        }
         while (m) {
             const int src = __ffs(m) - 1;
             const unsigned long long x = __shfl_sync(0xffffffffu, cand, src);
             if (x > thresh) insert(x, lane);  // warp-uniform branch (thresh and x are uniform)
             m &= m - 1;
         }
+    }
+    // KPL == 1 only: list <- the 32 largest of (list, 32 candidates).  Bitonic sort of the candidates
+    // (descending), elementwise max with the reversed list (a bitonic sequence holding the top 32),
+    // bitonic merge back to descending order.
+    __device__ __forceinline__ void merge32(unsigned long long v, int lane) {
+#pragma unroll
+        for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, j);
+                const bool desc = (kk == 32) || ((lane & kk) == 0);
+                const bool lower = (lane & j) == 0;
+                v = (lower == desc) ? (v > o ? v : o) : (v < o ? v : o);
+            }
+        }
+        const unsigned long long rev = __shfl_sync(0xffffffffu, k[0], 31 - lane);
+        v = v > rev ? v : rev;
+#pragma unroll
+        for (int j = 16; j > 0; j >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, j);
+            v = ((lane & j) == 0) ? (v > o ? v : o) : (v < o ? v : o);
+        }
+        k[0] = v;
+        thresh = __shfl_sync(0xffffffffu, v, (K - 1) & 31);
     }
 };
 
@@ -296,6 +452,63 @@ peak_tile_kernel(const float* __restrict__ heat, int r, int H, int W, int K, int
     }
 }
 
+// Fast variant of pass 1 for compile-time radii (see FastTile).
+template <int KPL, int R>
+__global__ void __launch_bounds__(kNmsThreads)
+peak_tile_fast_kernel(const float* __restrict__ heat, int H, int W, int K, int tiles_x, int tiles_per_plane,
+                      unsigned long long* __restrict__ cand) {
+    using T = FastTile<R>;
+    extern __shared__ __align__(16) int smem_i[];
+    int* s_key = smem_i;
+    int* s_col = smem_i + T::kPitch * T::kRows;
+    const int plane_id = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int y0 = (tile / tiles_x) * kTileH, x0 = (tile % tiles_x) * kTileW;
+    T::template stage_and_columns<false>(heat + (size_t)plane_id * H * W, H, W, y0, x0, 0.f, s_key, s_col);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpTopK<KPL> top;
+    top.init(K);
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int ty = pass * 16 + warp * 2 + (lane >> 4), q4 = lane & 15;
+        int mx[4];
+        T::row_max4(s_col, ty, q4, mx);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int kv = s_key[(ty + R) * T::kPitch + R + 4 * q4 + j];
+            const int y = y0 + ty, x = x0 + 4 * q4 + j;
+            unsigned long long key = 0ull;
+            if (y < H && x < W) {
+                // peak = heat * keep (wss/utils.py:11-13): the value itself where it equals the window
+                // maximum; otherwise heat*0, i.e. 0 for finite heat and NaN for NaN / +-inf heat
+                int pk;
+                if (kv == mx[j] && kv != kKeyNaN) pk = kv;
+                else pk = (kv == kKeyNaN || kv == 0x7f800000 || kv == (int)0x807fffff) ? kKeyNaN : 0;
+                key = ((unsigned long long)((unsigned)pk ^ 0x80000000u) << 32) |
+                      (unsigned long long)(0xffffffffu - (unsigned)(y * W + x));
+            }
+            top.offer(key, lane);
+        }
+    }
+    __syncthreads();
+    unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_i);
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) s_keys[warp * (32 * KPL) + i * 32 + lane] = top.k[i];
+    __syncthreads();
+    if (warp == 0) {
+        WarpTopK<KPL> fin;
+        fin.init(K);
+        for (int i = lane; i < kWarpsPerBlock * 32 * KPL; i += 32) fin.offer(s_keys[i], lane);
+        unsigned long long* dst = cand + ((size_t)plane_id * tiles_per_plane + tile) * K;
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+            const int gi = i * 32 + lane;
+            if (gi < K) dst[gi] = fin.k[i];
+        }
+    }
+}
+
 // Pass 2: one warp per plane merges the tile candidates and writes the sorted result.
 template <int KPL>
 __global__ void __launch_bounds__(32)
@@ -324,6 +537,33 @@ peak_merge_kernel(const unsigned long long* __restrict__ cand, int n_cand, int K
     }
 }
 
+template <int KPL, int R>
+static int launch_peak_tile_fast_R(const float* heat, unsigned long long* cand, int planes, int H, int W, int K,
+                                   int tiles_x, int tiles, cudaStream_t s) {
+    size_t smem = FastTile<R>::kSmem;
+    const size_t need_keys = sizeof(unsigned long long) * kWarpsPerBlock * 32 * KPL;
+    if (smem < need_keys) smem = need_keys;
+    cudaError_t e = cudaFuncSetAttribute(peak_tile_fast_kernel<KPL, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("peak_extract: smem attribute: %s", cudaGetErrorString(e));
+        return CL4_ECUDA;
+    }
+    peak_tile_fast_kernel<KPL, R><<<dim3(tiles, planes), kNmsThreads, smem, s>>>(heat, H, W, K, tiles_x, tiles, cand);
+    return check_launch("peak_tile_fast");
+}
+// returns 1 when the radius has no fast specialisation
+template <int KPL>
+static int launch_peak_tile_fast(const float* heat, unsigned long long* cand, int planes, int H, int W, int r, int K,
+                                 int tiles_x, int tiles, cudaStream_t s) {
+    switch (r) {
+        case 1: return launch_peak_tile_fast_R<KPL, 1>(heat, cand, planes, H, W, K, tiles_x, tiles, s);
+        case 2: return launch_peak_tile_fast_R<KPL, 2>(heat, cand, planes, H, W, K, tiles_x, tiles, s);
+        case 7: return launch_peak_tile_fast_R<KPL, 7>(heat, cand, planes, H, W, K, tiles_x, tiles, s);
+        case 20: return launch_peak_tile_fast_R<KPL, 20>(heat, cand, planes, H, W, K, tiles_x, tiles, s);
+    }
+    return 1;
+}
+
 template <int KPL>
 static int launch_peak(const float* heat, float* scores, int* ys, int* xs, unsigned long long* cand, int B, int C,
                        int H, int W, int r, int K, cudaStream_t s) {
@@ -337,11 +577,37 @@ static int launch_peak(const float* heat, float* scores, int* ys, int* xs, unsig
         set_error("peak_extract: smem attribute: %s", cudaGetErrorString(e));
         return CL4_ECUDA;
     }
-    peak_tile_kernel<KPL><<<dim3(tiles, B * C), kNmsThreads, smem, s>>>(heat, r, H, W, K, tiles_x, tiles, cand);
-    int rc = check_launch("peak_tile");
+    int rc = launch_peak_tile_fast<KPL>(heat, cand, B * C, H, W, r, K, tiles_x, tiles, s);
+    if (rc == 1) {  // no compile-time specialisation for this radius: generic kernel
+        peak_tile_kernel<KPL><<<dim3(tiles, B * C), kNmsThreads, smem, s>>>(heat, r, H, W, K, tiles_x, tiles, cand);
+        rc = check_launch("peak_tile");
+    }
     if (rc != CL4_OK) return rc;
     peak_merge_kernel<KPL><<<B * C, 32, 0, s>>>(cand, tiles * K, K, W, scores, ys, xs);
     return check_launch("peak_merge");
+}
+
+template <int R>
+static int launch_center_flags_fast_R(const float* heat, float thr, float min_value, int H, int W, int wpr,
+                                      uint32_t* words, dim3 grid, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(center_flags_fast_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)FastTile<R>::kSmem);
+    if (e != cudaSuccess) {
+        set_error("center_nms: smem attribute: %s", cudaGetErrorString(e));
+        return CL4_ECUDA;
+    }
+    center_flags_fast_kernel<R><<<grid, kNmsThreads, FastTile<R>::kSmem, s>>>(heat, thr, min_value, H, W, wpr, words);
+    return check_launch("center_flags_fast");
+}
+static int launch_center_flags_fast(const float* heat, float thr, float min_value, int r, int H, int W, int wpr,
+                                    uint32_t* words, dim3 grid, cudaStream_t s) {
+    switch (r) {
+        case 1: return launch_center_flags_fast_R<1>(heat, thr, min_value, H, W, wpr, words, grid, s);
+        case 2: return launch_center_flags_fast_R<2>(heat, thr, min_value, H, W, wpr, words, grid, s);
+        case 7: return launch_center_flags_fast_R<7>(heat, thr, min_value, H, W, wpr, words, grid, s);
+        case 20: return launch_center_flags_fast_R<20>(heat, thr, min_value, H, W, wpr, words, grid, s);
+    }
+    return 1;
 }
 
 int launch_center_compact(const uint32_t* words, int N, int H, int words_per_row, long long* ctr_out, int* count_out,
@@ -380,8 +646,11 @@ extern "C" int cl4_center_nms(const float* heat, float threshold, float min_valu
     cudaError_t e = cudaFuncSetAttribute(center_flags_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     CL4_REQUIRE(e == cudaSuccess, CL4_ECUDA, "center_nms: smem attribute: %s", cudaGetErrorString(e));
     dim3 grid(ceil_div(W, kTileW), ceil_div(H, kTileH), N);
-    center_flags_kernel<<<grid, kNmsThreads, smem, s>>>(heat, threshold, min_value, r, H, W, wpr, words);
-    int rc = check_launch("center_flags");
+    int rc = launch_center_flags_fast(heat, threshold, min_value, r, H, W, wpr, words, grid, s);
+    if (rc == 1) {  // no compile-time specialisation for this radius: generic kernel
+        center_flags_kernel<<<grid, kNmsThreads, smem, s>>>(heat, threshold, min_value, r, H, W, wpr, words);
+        rc = check_launch("center_flags");
+    }
     if (rc != CL4_OK) return rc;
     return launch_center_compact(words, N, H, wpr, ctr_out, count_out, max_out, row_off, s);
 }
