@@ -290,6 +290,9 @@ def main():
     pamr_bytes_iter = 4.0 * H * W * (3 + P + T * (P + 2 * C))      # per image
     pamr_flops = 2.0 * C * P * T * H * W
     per_img_s = stats["elapsed_s"] / (B * K_)
+    # dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch from the committed ncu --set full
+    # capture of this workload (profiles/r01_sweep_ncu_raw.csv); other workloads were not captured
+    traffic = 1.917e9 if args.workload == "voc_b16_c21_512" else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
         "ms_per_step": 1e3 * stats["elapsed_s"] / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -298,7 +301,7 @@ def main():
                    "nms_kernel": cfg["nms"], "threshold": cfg["thr"], "centres_per_image": cfg["Kc"],
                    "mask": "dense softmax over all classes", "l2": "inputs + scratch per step exceed L2 (no flush needed)"},
         "roofline": {"bound": "hbm", "kernel": "pamr_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": sweep_bytes, "mean_launch_ms": sweep_ms},
         "path_roofline": {"bytes_iter_frac_of_hbm": pamr_bytes_iter / per_img_s / 1e9 / peak,
                           "fp32_tflops": pamr_flops / per_img_s / 1e12, "fp32_frac_of_74.4": pamr_flops / per_img_s / 74.4e12},
