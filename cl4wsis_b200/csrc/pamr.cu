@@ -264,15 +264,13 @@ extern "C" int cl4_pamr_sweep(const float* w, const float* mask_in, float* mask_
 }
 
 extern "C" size_t cl4_pamr_scratch_bytes(int B, int K, int C, int H, int W, int D, int num_iter) {
-    (void)K;
-    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return 0;
-    const size_t HW = (size_t)H * W;
-    (void)HW;
+    if (B <= 0 || K <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return 0;
     const size_t wbytes = cl4::align_up(sizeof(float) * cl4::tiled_weight_elems(B, H, W, D), 256);
     // padded path: one replicate-padded copy of the input (+ a second ping-pong buffer from 2 sweeps on);
     // generic path: one plain ping-pong buffer.  The padded layout is the larger of the two.
     const size_t padded = cl4::align_up(sizeof(float) * (size_t)B * C * cl4::padded_plane_elems(H, W), 256);
-    return wbytes + (num_iter >= 2 ? 2 : 1) * padded;
+    const size_t padded_img = cl4::align_up(sizeof(float) * (size_t)B * K * cl4::padded_plane_elems(H, W), 256);
+    return wbytes + (num_iter >= 2 ? 2 : 1) * padded + padded_img;
 }
 
 extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, float* mask_out, void* scratch,
@@ -314,7 +312,14 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
     // CL4_SWEEP=v1 forces the register/L1 kernel (A/B timing and tests of the generic path)
     const char* force = getenv("CL4_SWEEP");
     const bool use_tma = !(force && strcmp(force, "v1") == 0) && sweep_tma_applicable(H, W, dil, D);
-    rc = dispatch_D<WeightsLauncher>(D, img, wts, B, K, H, W, dil, use_tma ? 1 : 0, s);
+    if (use_tma && weights_tma_applicable(K)) {
+        // image -> replicate-padded copy (scratch, after the mask buffers) -> TMA-staged weights kernel
+        float* pimg = reinterpret_cast<float*>(base + wbytes + (num_iter >= 2 ? 2 : 1) * padded);
+        rc = launch_pad_copy(img, pimg, (long long)B * K, H, W, s);
+        if (rc == CL4_OK) rc = launch_weights_tma(pimg, wts, B, K, H, W, dil, D, s);
+    } else {
+        rc = dispatch_D<WeightsLauncher>(D, img, wts, B, K, H, W, dil, use_tma ? 1 : 0, s);
+    }
     if (rc != CL4_OK) return rc;
     if (use_tma) {
         // replicate-padded ping-pong: in -> A -> B -> A ... -> out (plain layout)

@@ -14,6 +14,10 @@ size_t padded_plane_elems(int H, int W);
 size_t tiled_weight_elems(int B, int H, int W, int D);  // weights in [tile][8D][32][32] layout (>= B*8D*H*W)
 int launch_pad_copy(const float* src, float* dst, long long planes, int H, int W, cudaStream_t s);
 int launch_pad_frame(float* buf, long long planes, int H, int W, cudaStream_t s);  // replicate frame, in place
+// Affinity weights from a replicate-padded image [B*K][H+48][W+48] into the tile-major layout; K <= 3.
+bool weights_tma_applicable(int K);
+int launch_weights_tma(const float* padded_img, float* w, int B, int K, int H, int W, const Dilations& dil, int D,
+                       cudaStream_t s);
 // w: tile-major weights (tiled_weight_elems), as written by the weights kernel in tiled mode
 int launch_sweep_tma(const float* w, const float* padded_in, float* out, int out_padded, int B, int C, int H, int W,
                      const Dilations& dil, int D, cudaStream_t s);

@@ -259,6 +259,92 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
 }
 
 // ---------------------------------------------------------------------------------------------
+// Affinity weights from a replicate-padded image (reference wss/modules.py:141-145), one CTA per
+// 32x32 tile: the K (<= 3) 80x80 channel windows arrive by TMA, every neighbour read is an LDS with
+// an immediate offset, and each thread walks its four pixels one after the other (registers hold
+// one pixel's 8D deviations and 8D logits).  Writes the tile-major float4 layout the sweep reads.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWeightsMaxK = 3;
+
+template <int D, class DS>
+__global__ void __launch_bounds__(256, 2)
+pamr_weights_tma_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ wts, int K, int tiles_x,
+                        int tiles_per_img, Dilations dil) {
+    constexpr int P = 8 * D;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float* win = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWeightsMaxK * kStageBytes);
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const TileCoord tc = tile_coord(blockIdx.x, tiles_x, tiles_per_img);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(bar, (uint32_t)(K * kStageBytes));
+        for (int k = 0; k < K; ++k) tma_load_3d(win + (size_t)k * (kBox * kBox), &tmap, bar, tc.x0, tc.y0, tc.b * K + k);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    float4* o = reinterpret_cast<float4*>(wts) + (size_t)blockIdx.x * (P / 4 * kTile * kTile) + lane;
+    const float invK = 1.f / (float)K;
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        const int row = wrp + 8 * i;
+        const float* sp0 = win + (row + kHalo) * kBox + lane + kHalo;
+        float logit[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) logit[p] = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+            const float* sp = sp0 + k * (kBox * kBox);
+            const float c = sp[0];
+            float dlt[P];  // neighbour - centre; the D centre samples of LocalStDev contribute zeros
+#pragma unroll
+            for (int di = 0; di < D; ++di) {
+                const int d = DS::kStatic ? DS::get(di) : dil.d[di];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int dy = (j < 3) ? -1 : ((j < 5) ? 0 : 1);
+                    const int dx = (j < 3) ? (j - 1) : ((j == 3) ? -1 : ((j == 4) ? 1 : (j - 6)));
+                    dlt[di * 8 + j] = sp[dy * d * kBox + dx * d] - c;
+                }
+            }
+            float s1 = 0.f;
+#pragma unroll
+            for (int p = 0; p < P; ++p) s1 += dlt[p];
+            const float mean = s1 * (1.f / (float)(9 * D));
+            float ss = (float)D * mean * mean;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const float t = dlt[p] - mean;
+                ss = fmaf(t, t, ss);
+            }
+            const float sd = sqrtf(ss * (1.f / (float)(9 * D - 1)));
+            const float ninv = -1.f / (1e-8f + 0.1f * sd);
+#pragma unroll
+            for (int p = 0; p < P; ++p) logit[p] = fmaf(fabsf(dlt[p]), ninv, logit[p]);
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            logit[p] *= invK;
+            mx = fmaxf(mx, logit[p]);
+        }
+        float z = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            logit[p] = __expf(logit[p] - mx);
+            z += logit[p];
+        }
+        const float rz = 1.f / z;
+#pragma unroll
+        for (int g = 0; g < P / 4; ++g)
+            o[(size_t)g * (kTile * kTile) + row * kTile] =
+                make_float4(logit[4 * g] * rz, logit[4 * g + 1] * rz, logit[4 * g + 2] * rz, logit[4 * g + 3] * rz);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Replicate-padded planes.
 // ---------------------------------------------------------------------------------------------
 // dst [planes][H+2*pad][W+2*pad] <- replicate-pad(src [planes][H][W]).  One thread per float4 of a
@@ -379,6 +465,62 @@ int launch_pad_frame(float* buf, long long planes, int H, int W, cudaStream_t s)
     dim3 grid(bands_blocks + ceil_div(H, 256), (unsigned)planes);
     pamr_pad_frame_kernel<<<grid, 256, 0, s>>>(buf, H, W, bands_blocks);
     return check_launch("pamr_pad_frame");
+}
+
+template <int D, class DS>
+static int launch_weights_one(const CUtensorMap& tmap, float* w, int K, int tiles_x, int tiles_per_img, int n_tiles,
+                              const Dilations& dil, cudaStream_t s) {
+    auto kern = pamr_weights_tma_kernel<D, DS>;
+    const size_t smem = (size_t)kWeightsMaxK * kStageBytes + 64;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("pamr_weights_tma: smem attribute: %s", cudaGetErrorString(e));
+            return CL4_ECUDA;
+        }
+        attr_done = true;
+    }
+    kern<<<n_tiles, 256, smem, s>>>(tmap, w, K, tiles_x, tiles_per_img, dil);
+    return check_launch("pamr_weights_tma");
+}
+
+template <int D>
+static int launch_weights_D(const CUtensorMap& tmap, float* w, int K, int tiles_x, int tiles_per_img, int n_tiles,
+                            const Dilations& dil, cudaStream_t s) {
+    bool voc6 = (D == 6), voc5 = (D == 5);
+    for (int i = 0; i < D && i < 6; ++i) {
+        voc6 = voc6 && dil.d[i] == DilVoc6::get(i);
+        voc5 = voc5 && dil.d[i] == DilVoc5::get(i);
+    }
+    if (D == 6 && voc6) return launch_weights_one<6, DilVoc6>(tmap, w, K, tiles_x, tiles_per_img, n_tiles, dil, s);
+    if (D == 5 && voc5) return launch_weights_one<5, DilVoc5>(tmap, w, K, tiles_x, tiles_per_img, n_tiles, dil, s);
+    return launch_weights_one<D, DilRuntime>(tmap, w, K, tiles_x, tiles_per_img, n_tiles, dil, s);
+}
+
+bool weights_tma_applicable(int K) { return K >= 1 && K <= kWeightsMaxK; }
+
+// padded_img: [B*K][H+48][W+48] replicate-padded image; w: tile-major weights
+int launch_weights_tma(const float* padded_img, float* w, int B, int K, int H, int W, const Dilations& dil, int D,
+                       cudaStream_t s) {
+    CUtensorMap tmap;
+    const int rc = encode_tmap_3d_f32(&tmap, padded_img, W + 2 * kHalo, H + 2 * kHalo, (long long)B * K, kBox, kBox);
+    if (rc != 0) {
+        set_error("pamr_weights_tma: cuTensorMapEncodeTiled failed (%d)", rc);
+        return CL4_ECUDA;
+    }
+    const int tiles_x = ceil_div(W, kTile), tiles_y = ceil_div(H, kTile);
+    const int n_tiles = B * tiles_x * tiles_y;
+    switch (D) {
+        case 1: return launch_weights_D<1>(tmap, w, K, tiles_x, tiles_x * tiles_y, n_tiles, dil, s);
+        case 2: return launch_weights_D<2>(tmap, w, K, tiles_x, tiles_x * tiles_y, n_tiles, dil, s);
+        case 3: return launch_weights_D<3>(tmap, w, K, tiles_x, tiles_x * tiles_y, n_tiles, dil, s);
+        case 4: return launch_weights_D<4>(tmap, w, K, tiles_x, tiles_x * tiles_y, n_tiles, dil, s);
+        case 5: return launch_weights_D<5>(tmap, w, K, tiles_x, tiles_x * tiles_y, n_tiles, dil, s);
+        case 6: return launch_weights_D<6>(tmap, w, K, tiles_x, tiles_x * tiles_y, n_tiles, dil, s);
+    }
+    set_error("pamr_weights_tma: bad D=%d", D);
+    return CL4_EUNSUPPORTED;
 }
 
 template <int D, class DS>

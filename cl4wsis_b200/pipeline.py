@@ -36,8 +36,8 @@ class PseudoLabelStep:
         self.ids = torch.empty((B, H, W), dtype=torch.int64, device=dev)
         self.centers = torch.zeros((B, self.max_centers, 2), dtype=torch.int64, device=dev)
         self.counts = torch.zeros((B,), dtype=torch.int32, device=dev)
-        # launches per step: weights, pad copy, num_iter sweeps, num_iter-1 frame rewrites, 2 NMS, grouping
-        self.launches_per_step = 1 + 1 + self.num_iter + max(self.num_iter - 1, 0) + 2 + 1
+        # launches per step: image pad, weights, mask pad, num_iter sweeps, num_iter-1 frame rewrites, 2 NMS, grouping
+        self.launches_per_step = 1 + 1 + 1 + self.num_iter + max(self.num_iter - 1, 0) + 2 + 1
 
     def run(self, img, mask, heat, offsets, fg=None, stream=None, sweep_events=None):
         """All arguments are contiguous fp32 CUDA tensors: img [B,K,H,W], mask [B,C,H,W],

@@ -39,10 +39,10 @@ def test_ctypes_table_matches_header():
 
 def test_abi_version_and_scratch_queries(lib):
     assert lib.cl4_abi_version() == 1
-    # pure host arithmetic, no CUDA call: weights [B,48,H,W] + two replicate-padded mask buffers
+    # pure host arithmetic, no CUDA call: weights [B,48,H,W] + two replicate-padded mask buffers + the padded image
     n = lib.cl4_pamr_scratch_bytes(16, 3, 21, 512, 512, 6, 10)
-    assert n == 4 * 16 * 512 * 512 * 48 + 2 * 4 * 16 * 21 * 560 * 560
-    assert lib.cl4_pamr_scratch_bytes(16, 3, 21, 512, 512, 6, 1) == 4 * 16 * 512 * 512 * 48 + 4 * 16 * 21 * 560 * 560
+    assert n == 4 * 16 * 512 * 512 * 48 + 2 * 4 * 16 * 21 * 560 * 560 + 4 * 16 * 3 * 560 * 560
+    assert lib.cl4_pamr_scratch_bytes(16, 3, 21, 512, 512, 6, 1) == 4 * 16 * 512 * 512 * 48 + 4 * 16 * (21 + 3) * 560 * 560
     assert lib.cl4_center_nms_scratch_bytes(1, 512, 512) >= 512 * 16 * 4 + 512 * 4
     assert lib.cl4_peak_extract_scratch_bytes(2, 3, 64, 64, 15, 25) == 2 * 3 * 2 * 25 * 8
 
