@@ -24,6 +24,8 @@ _flt = ctypes.c_float
 SIGNATURES = {
     "cl4_abi_version": (_int, []),
     "cl4_last_error": (ctypes.c_char_p, []),
+    "cl4_local_affinity": (_int, [_vp, _vp, _int, _int, _int, ctypes.POINTER(_int), _int, _int, _vp]),
+    "cl4_local_stdev": (_int, [_vp, _vp, _int, _int, _int, ctypes.POINTER(_int), _int, _vp]),
     "cl4_resize_bilinear_ac": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp]),
     "cl4_pamr_weights": (_int, [_vp, _vp, _int, _int, _int, _int, ctypes.POINTER(_int), _int, _vp]),
     "cl4_pamr_sweep": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, ctypes.POINTER(_int), _int, _vp]),

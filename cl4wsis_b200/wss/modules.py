@@ -5,6 +5,10 @@ The module keeps the reference's constructor, attribute and buffer names
 ``dilations`` attribute — wss/modules.py:19-45, :65-83, :86-102) so that
 ``state_dict()`` of anything embedding it is unchanged, but the
 forward pass never touches those buffers: it calls ``cl4_pamr_forward``.
+
+The helper stencils ``LocalAffinity``, ``LocalAffinityAbs``, ``LocalAffinityCopy`` and
+``LocalStDev`` (wss/modules.py:17-119) are drop-ins too: their ``forward`` runs the
+stand-alone kernels ``cl4_local_affinity`` / ``cl4_local_stdev``.
 """
 import torch
 import torch.nn as nn
@@ -14,51 +18,94 @@ from .. import _lib
 _TAPS8 = [(0, 0), (0, 1), (0, 2), (1, 0), (1, 2), (2, 0), (2, 1), (2, 2)]
 
 
-class _Stencil(nn.Module):
-    """Holds the 3x3 shift-stencil buffer of the reference helper modules (state only)."""
+class LocalAffinity(nn.Module):
+    """``LocalAffinity(dilations).forward(x)`` — wss/modules.py:17-62: centre minus neighbour for
+    the 8 neighbours of every dilation, replicate padding.  x [B,K,H,W] -> [B,K,8*D,H,W]."""
+
+    _mode = 0  # cl4_local_affinity mode: x - shift_p(x)
 
     def __init__(self, dilations=[1]):
         super().__init__()
         self.dilations = dilations
-        self.register_buffer("kernel", self._init_aff())
-
-    def _init_aff(self):
-        raise NotImplementedError
-
-
-class LocalAffinity(_Stencil):
-    """centre minus neighbour (wss/modules.py:26-45)."""
+        weight = self._init_aff()
+        self.register_buffer("kernel", weight)
 
     def _init_aff(self):
         k = torch.zeros(8, 1, 3, 3)
         for i, (r, c) in enumerate(_TAPS8):
             k[i, 0, 1, 1] = 1
             k[i, 0, r, c] = -1
+        self.weight_check = k.clone()
         return k
+
+    def _check_kernel(self, x):
+        # wss/modules.py:49-50: the stencil buffer must still equal its construction-time copy
+        self.weight_check = self.weight_check.type_as(x)
+        assert torch.all(self.weight_check.eq(self.kernel))
+
+    @torch.no_grad()
+    def forward(self, x):
+        self._check_kernel(x)
+        return _local_affinity(x, self.dilations, self._mode)
 
 
 class LocalAffinityAbs(LocalAffinity):
     """|centre - neighbour| (wss/modules.py:115-119)."""
 
+    _mode = 1
 
-class LocalAffinityCopy(_Stencil):
+
+class LocalAffinityCopy(LocalAffinity):
     """neighbour gather (wss/modules.py:65-83)."""
+
+    _mode = 2
 
     def _init_aff(self):
         k = torch.zeros(8, 1, 3, 3)
         for i, (r, c) in enumerate(_TAPS8):
             k[i, 0, r, c] = 1
+        self.weight_check = k.clone()
         return k
 
 
-class LocalStDev(_Stencil):
-    """9-tap gather feeding the unbiased std (wss/modules.py:86-112)."""
+class LocalStDev(LocalAffinity):
+    """Unbiased std over the 9 taps (centre included) of every dilation — wss/modules.py:86-112.
+    x [B,K,H,W] -> [B,K,1,H,W]."""
 
     def _init_aff(self):
         k = torch.zeros(9, 1, 3, 3)
         for i in range(9):
             k[i, 0, i // 3, i % 3] = 1
+        self.weight_check = k.clone()
         return k
+
+    @torch.no_grad()
+    def forward(self, x):
+        self._check_kernel(x)
+        lib = _lib.load()
+        x, (B, K, H, W), dil = _stencil_input(x, self.dilations)
+        out = torch.empty((B, K, 1, H, W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.cl4_local_stdev(_lib.ptr(x), _lib.ptr(out), B * K, H, W, _lib.int_array(dil), len(dil),
+                                           _lib.stream_ptr(x.device)), "LocalStDev")
+        return out
+
+
+def _stencil_input(x, dilations):
+    x = _as_f32(x, "x")
+    if x.dim() != 4:
+        raise ValueError("expected x [B,K,H,W]")
+    return x, tuple(x.shape), [int(d) for d in dilations]
+
+
+def _local_affinity(x, dilations, mode):
+    lib = _lib.load()
+    x, (B, K, H, W), dil = _stencil_input(x, dilations)
+    out = torch.empty((B, K, 8 * len(dil), H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.cl4_local_affinity(_lib.ptr(x), _lib.ptr(out), B * K, H, W, _lib.int_array(dil), len(dil),
+                                          int(mode), _lib.stream_ptr(x.device)), "LocalAffinity")
+    return out
 
 
 class PAMR(nn.Module):

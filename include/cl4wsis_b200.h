@@ -45,6 +45,19 @@ const char* cl4_last_error(void);
  * PAMR — wss/modules.py:122-152 (class PAMR), stencils :17-119.
  * ------------------------------------------------------------------------- */
 
+/* Stand-alone forwards of the helper stencils PAMR is built from (the fused PAMR entry
+ * points below never materialise these tensors).  x [planes,H,W] (planes = B*K):
+ *   cl4_local_affinity, mode 0: LocalAffinity.forward      x - shift_p(x)    wss/modules.py:47-62
+ *                       mode 1: LocalAffinityAbs.forward   |x - shift_p(x)|  wss/modules.py:115-119
+ *                       mode 2: LocalAffinityCopy.forward  shift_p(x)        wss/modules.py:65-83
+ *     -> out [planes,8*D,H,W], p = dilation_index*8 + tap (tap order :30-40), replicate padding :57;
+ *   cl4_local_stdev: LocalStDev.forward, unbiased std over the 9*D samples   wss/modules.py:86-112
+ *     -> out [planes,1,H,W]. */
+int cl4_local_affinity(const float* x, float* out, int planes, int H, int W, const int* dilations, int D,
+                       int mode, cl4_stream_t stream);
+int cl4_local_stdev(const float* x, float* out, int planes, int H, int W, const int* dilations, int D,
+                    cl4_stream_t stream);
+
 /* F.interpolate(mask, size=(H,W), mode="bilinear", align_corners=True), the first
  * line of PAMR.forward (wss/modules.py:134).  in [planes,h,w] -> out [planes,H,W]. */
 int cl4_resize_bilinear_ac(const float* in, float* out, int planes, int h, int w, int H, int W,

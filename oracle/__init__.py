@@ -5,6 +5,6 @@ Importable only from tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s
 ``cl4wsis_b200`` never imports this.
 """
 from .oracle import (  # noqa: F401
-    build, pamr, pamr_weights, peak_extract, find_instance_center, group_pixels,
+    build, pamr, pamr_weights, local_affinity, local_stdev, peak_extract, find_instance_center, group_pixels,
     get_instance_segmentation, cluster_peaks, resize_bilinear_ac, num_threads, set_num_threads,
 )

@@ -88,6 +88,66 @@ int cl4o_resize_bilinear_ac(const float* in, float* out, int planes, int h, int 
 }
 
 /* ------------------------------------------------------------------------- *
+ * Helper stencils on their own: wss/modules.py:17-119.
+ *   mode 0  LocalAffinity.forward      x - shift_p(x)   (:47-62; conv2d with the
+ *           +1 centre / -1 neighbour kernel of :26-45 = one rounded subtraction)
+ *   mode 1  LocalAffinityAbs.forward   |x - shift_p(x)| (:115-119)
+ *   mode 2  LocalAffinityCopy.forward  shift_p(x)       (:65-83)
+ * x [planes,H,W] -> out [planes,8*D,H,W], p = dilation_index*8 + tap.
+ * ------------------------------------------------------------------------- */
+int cl4o_local_affinity(const float* x, float* out, int planes, int H, int W, const int* dil, int D, int mode) {
+    if (planes < 0 || H <= 0 || W <= 0 || D <= 0 || mode < 0 || mode > 2) return CL4O_EINVAL;
+    const size_t HW = (size_t)H * W;
+#pragma omp parallel for schedule(static)
+    for (int pl = 0; pl < planes; ++pl) {
+        const float* src = x + (size_t)pl * HW;
+        for (int di = 0; di < D; ++di)
+            for (int t = 0; t < 8; ++t) {
+                float* dst = out + ((size_t)pl * 8 * D + di * 8 + t) * HW;
+                for (int y = 0; y < H; ++y) {
+                    const int yy = clampi(y + TAP_DY[t] * dil[di], 0, H - 1);
+                    for (int xx = 0; xx < W; ++xx) {
+                        const float nb = src[(size_t)yy * W + clampi(xx + TAP_DX[t] * dil[di], 0, W - 1)];
+                        const float c = src[(size_t)y * W + xx];
+                        dst[(size_t)y * W + xx] = mode == 2 ? nb : (mode == 1 ? fabsf(c - nb) : c - nb);
+                    }
+                }
+            }
+    }
+    return CL4O_OK;
+}
+
+/* LocalStDev.forward: wss/modules.py:86-112 — x.std(2) (unbiased) over the 9*D
+ * gathered samples, the centre once per dilation.  x [planes,H,W] -> out [planes,H,W]. */
+int cl4o_local_stdev(const float* x, float* out, int planes, int H, int W, const int* dil, int D) {
+    if (planes < 0 || H <= 0 || W <= 0 || D <= 0) return CL4O_EINVAL;
+    const size_t HW = (size_t)H * W;
+    const int N = 9 * D;
+#pragma omp parallel for schedule(static)
+    for (int pl = 0; pl < planes; ++pl) {
+        const float* src = x + (size_t)pl * HW;
+        for (int y = 0; y < H; ++y)
+            for (int xx = 0; xx < W; ++xx) {
+                double s = 0.0;
+                for (int di = 0; di < D; ++di)
+                    for (int t = 0; t < 9; ++t)
+                        s += (double)src[(size_t)clampi(y + TAP9_DY[t] * dil[di], 0, H - 1) * W +
+                                         clampi(xx + TAP9_DX[t] * dil[di], 0, W - 1)];
+                const double mean = s / N;
+                double ss = 0.0;
+                for (int di = 0; di < D; ++di)
+                    for (int t = 0; t < 9; ++t) {
+                        const double dlt = (double)src[(size_t)clampi(y + TAP9_DY[t] * dil[di], 0, H - 1) * W +
+                                                       clampi(xx + TAP9_DX[t] * dil[di], 0, W - 1)] - mean;
+                        ss += dlt * dlt;
+                    }
+                out[(size_t)pl * HW + (size_t)y * W + xx] = (float)sqrt(ss / (double)(N - 1));
+            }
+    }
+    return CL4O_OK;
+}
+
+/* ------------------------------------------------------------------------- *
  * PAMR affinity weights: wss/modules.py:141-145.
  *   x_std = LocalStDev(x)           unbiased std over the 9*D samples (:86-112)
  *   a     = |x - shift_p(x)|        LocalAffinityAbs (:115-119 over :47-62)

@@ -43,6 +43,8 @@ def _load():
         lib.cl4o_num_threads.restype = ctypes.c_int
         lib.cl4o_set_num_threads.argtypes = [ctypes.c_int]
         lib.cl4o_resize_bilinear_ac.argtypes = [_f32p, _f32p] + [ctypes.c_int] * 5
+        lib.cl4o_local_affinity.argtypes = [_f32p, _f32p] + [ctypes.c_int] * 3 + [_i32p, ctypes.c_int, ctypes.c_int]
+        lib.cl4o_local_stdev.argtypes = [_f32p, _f32p] + [ctypes.c_int] * 3 + [_i32p, ctypes.c_int]
         lib.cl4o_pamr_weights.argtypes = [_f32p, _f32p] + [ctypes.c_int] * 4 + [_i32p, ctypes.c_int]
         lib.cl4o_pamr.argtypes = [_f32p, _f32p, _f32p] + [ctypes.c_int] * 7 + [_i32p, ctypes.c_int, ctypes.c_int]
         lib.cl4o_peak_extract.argtypes = [_f32p, _f32p, _i32p, _i32p] + [ctypes.c_int] * 6
@@ -82,6 +84,29 @@ def resize_bilinear_ac(x, size):
     out = np.empty(x.shape[:-2] + (H, W), np.float32)
     planes = int(np.prod(x.shape[:-2], dtype=np.int64))
     _check(_load().cl4o_resize_bilinear_ac(_ptr(x, _f32p), _ptr(out, _f32p), planes, h, w, H, W), "resize")
+    return out
+
+
+def local_affinity(x, dilations, mode=0):
+    """LocalAffinity (mode 0), LocalAffinityAbs (1), LocalAffinityCopy (2) .forward(x):
+    wss/modules.py:47-62, :115-119, :65-83.  x [B,K,H,W] -> [B,K,8*D,H,W]."""
+    x = _f32(x)
+    B, K, H, W = x.shape
+    dil = np.ascontiguousarray(dilations, dtype=np.int32)
+    out = np.empty((B, K, 8 * len(dil), H, W), np.float32)
+    _check(_load().cl4o_local_affinity(_ptr(x, _f32p), _ptr(out, _f32p), B * K, H, W, _ptr(dil, _i32p), len(dil),
+                                       int(mode)), "local_affinity")
+    return out
+
+
+def local_stdev(x, dilations):
+    """LocalStDev.forward(x): wss/modules.py:86-112.  x [B,K,H,W] -> [B,K,1,H,W]."""
+    x = _f32(x)
+    B, K, H, W = x.shape
+    dil = np.ascontiguousarray(dilations, dtype=np.int32)
+    out = np.empty((B, K, 1, H, W), np.float32)
+    _check(_load().cl4o_local_stdev(_ptr(x, _f32p), _ptr(out, _f32p), B * K, H, W, _ptr(dil, _i32p), len(dil)),
+           "local_stdev")
     return out
 
 

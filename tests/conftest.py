@@ -20,6 +20,18 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_more():
+    """Per-section fixtures of tests/golden/make_golden_more.py: golden_more("stencils") -> npz."""
+    cache = {}
+
+    def get(section):
+        if section not in cache:
+            cache[section] = np.load(os.path.join(ROOT, "tests", "golden", f"reference_golden_{section}.npz"))
+        return cache[section]
+    return get
+
+
+@pytest.fixture(scope="session")
 def oracle():
     import oracle as o
     o.build()

@@ -29,6 +29,38 @@ def cuda(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
+# --------------------------------------------------------------------------- helper stencils
+@pytest.mark.parametrize("name", ["st_d6", "st_d5", "st_d1", "st_tiny", "st_odd"])
+def test_helper_stencils_golden(cl4, golden_more, name):
+    """wss/modules.py:17-119 drop-ins against reference outputs: differences / gathers bit-exact."""
+    from cl4wsis_b200.wss import modules as wm
+    g = golden_more("stencils")
+    x, dil = cuda(g[name + "__x"]), g[name + "__dil"].tolist()
+    for cls, key in ((wm.LocalAffinity, "aff"), (wm.LocalAffinityAbs, "abs"), (wm.LocalAffinityCopy, "copy")):
+        got = cls(dil).cuda()(x).cpu().numpy()
+        assert got.shape == g[f"{name}__{key}"].shape and got.dtype == np.float32
+        assert np.array_equal(got, g[f"{name}__{key}"]), (name, key)
+    got = wm.LocalStDev(dil).cuda()(x).cpu().numpy()
+    assert got.shape == g[name + "__std"].shape
+    np.testing.assert_allclose(got, g[name + "__std"], rtol=1e-5, atol=1e-7)
+
+
+def test_helper_stencils_large_vs_oracle(cl4, oracle):
+    from cl4wsis_b200.wss import modules as wm
+    rng = np.random.default_rng(7)
+    x = rng.random((2, 3, 200, 260)).astype(np.float32)
+    dil = [1, 2, 4, 8, 12, 24]
+    for mode, cls in enumerate((wm.LocalAffinity, wm.LocalAffinityAbs, wm.LocalAffinityCopy)):
+        assert np.array_equal(cls(dil).cuda()(cuda(x)).cpu().numpy(), oracle.local_affinity(x, dil, mode))
+    np.testing.assert_allclose(wm.LocalStDev(dil).cuda()(cuda(x)).cpu().numpy(), oracle.local_stdev(x, dil),
+                               rtol=1e-5, atol=1e-7)
+    # the reference's self-check (wss/modules.py:49-50): a modified stencil buffer trips the assert
+    mod = wm.LocalAffinity(dil).cuda()
+    mod.kernel[0, 0, 0, 0] = 5.0
+    with pytest.raises(AssertionError):
+        mod(cuda(x))
+
+
 # --------------------------------------------------------------------------- PAMR
 @pytest.mark.parametrize("name", PAMR_CASES)
 def test_pamr_golden(cl4, golden, name):

@@ -109,3 +109,18 @@ def test_get_instance_segmentation_matches_reference(golden, oracle):
         assert np.array_equal(heat_after, golden[f"inst_{i}__heat_after"]), i
         seen_beta += beta > 0
     assert n >= 5 and seen_beta >= 2
+
+
+STENCIL_CASES = ["st_d6", "st_d5", "st_d1", "st_tiny", "st_odd"]
+
+
+@pytest.mark.parametrize("name", STENCIL_CASES)
+def test_helper_stencils_match_reference(golden_more, oracle, name):
+    """LocalAffinity / Abs / Copy are single rounded operations: bit-exact.  LocalStDev: rtol 1e-5."""
+    g = golden_more("stencils")
+    x, dil = g[name + "__x"], g[name + "__dil"].tolist()
+    for mode, key in ((0, "aff"), (1, "abs"), (2, "copy")):
+        got = oracle.local_affinity(x, dil, mode)
+        assert got.shape == g[f"{name}__{key}"].shape
+        assert np.array_equal(got, g[f"{name}__{key}"]), (name, key)
+    np.testing.assert_allclose(oracle.local_stdev(x, dil), g[name + "__std"], rtol=1e-5, atol=1e-7)
