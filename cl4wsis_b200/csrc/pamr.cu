@@ -309,9 +309,20 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
     const size_t padded = align_up(sizeof(float) * (size_t)B * C * padded_plane_elems(H, W), 256);
     float* bufA = reinterpret_cast<float*>(base + wbytes);
     float* bufB = reinterpret_cast<float*>(base + wbytes + padded);
-    // CL4_SWEEP=v1 forces the register/L1 kernel (A/B timing and tests of the generic path)
+    // CL4_SWEEP=v1 forces the register/L1 kernel, CL4_SWEEP=tma skips the fused small-map kernel
+    // (A/B timing and tests of the other paths)
     const char* force = getenv("CL4_SWEEP");
-    const bool use_tma = !(force && strcmp(force, "v1") == 0) && sweep_tma_applicable(H, W, dil, D);
+    const bool force_v1 = force && strcmp(force, "v1") == 0, force_tma = force && strcmp(force, "tma") == 0;
+    if (!force_v1 && !force_tma && pamr_fused_applicable(H, W, dil, D)) {
+        // small maps (the trainer's feature resolution): weights, then every iteration in one launch
+        rc = dispatch_D<WeightsLauncher>(D, img, wts, B, K, H, W, dil, 1, s);
+        if (rc != CL4_OK) return rc;
+        if ((rc = record(ev_sweeps_begin)) != CL4_OK) return rc;
+        rc = launch_pamr_fused(wts, mask_in, mask_out, B, C, H, W, num_iter, dil, D, s);
+        if (rc != CL4_OK) return rc;
+        return record(ev_sweeps_end);
+    }
+    const bool use_tma = !force_v1 && sweep_tma_applicable(H, W, dil, D);
     if (use_tma && weights_tma_applicable(K)) {
         // image -> replicate-padded copy (scratch, after the mask buffers) -> TMA-staged weights kernel
         float* pimg = reinterpret_cast<float*>(base + wbytes + (num_iter >= 2 ? 2 : 1) * padded);

@@ -1,0 +1,217 @@
+// PAMR propagation with EVERY iteration on-chip, for maps of at most 64 x 64 pixels — the
+// resolution PAMR really runs at inside the trainer (32 x 32 at crop 512 / stride 16, 56 x 56 for
+// coco-voc: train.py:376-379).  Reference: wss/modules.py:147-149, num_iter times.
+//
+// One CTA owns `cpb` classes of one image for all iterations.  Classes are independent in PAMR
+// (they only share the affinity weights), so CTAs never communicate.  Per class the CTA keeps two
+// replicate-padded planes (ping-pong) in shared memory: the clamped neighbour of wss/modules.py:57
+// is an ordinary in-bounds LDS at an immediate offset, exactly as in the HBM-resident TMA sweep
+// (pamr_tma.cu), whose inner loop (sweep_class) and thread mapping this kernel shares:
+//   * a thread owns 4 pixels of one column, 4 rows apart, of a 32 x 32 tile and keeps their
+//     4 x 8D weights in registers for all classes and — when the map is one tile — all iterations;
+//   * maps of 2-4 tiles re-read the tile-major weights from L2 at each tile switch, software-
+//     pipelined into the last class pass of the previous tile;
+//   * after each iteration the 24-pixel frame of the new planes is rewritten from their interior.
+// HBM traffic is the minimum: masks in once, masks out once, weights once per CTA (L2 hits after the
+// first CTA of an image).  The bound is shared-memory bandwidth (143 LDS per 192 FFMA).
+#include "common.cuh"
+#include "pamr_internal.cuh"
+#include "pamr_sweep.cuh"
+
+namespace cl4 {
+
+constexpr int kFusedMaxDim = 64;
+
+template <int D, class DS, int PITCH>
+__global__ void __launch_bounds__(kSweepThreads, 1)
+pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_in, float* __restrict__ mask_out,
+                  int C, int H, int W, int cpb, int num_iter, Dilations dil) {
+    constexpr int P = 8 * D;
+    constexpr int kPlane = PITCH * PITCH;  // PITCH rows of PITCH floats
+    extern __shared__ __align__(16) float smem[];
+
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int tx = lane;
+    const int ty = (wrp >> 2) * 16 + (wrp & 3);  // rows ty + 4*i
+    const int b = blockIdx.y;
+    const int c0 = blockIdx.x * cpb;
+    const int nc = min(cpb, C - c0);
+    const int tiles_x = ceil_div(W, kTile), tiles_y = ceil_div(H, kTile), n_tiles = tiles_x * tiles_y;
+    const int Hp = H + 2 * kHalo, Wp = W + 2 * kHalo;
+    const size_t HW = (size_t)H * W;
+
+    // planes: [class][ping-pong][PITCH][PITCH]
+    auto plane = [&](int c, int which) -> float* { return smem + (size_t)(c * 2 + which) * kPlane; };
+
+    // ---- stage the input masks as replicate-padded planes
+    for (int c = 0; c < nc; ++c) {
+        const float* src = mask_in + ((size_t)b * C + c0 + c) * HW;
+        float* dst = plane(c, 0);
+        for (int i = tid; i < Hp * Wp; i += kSweepThreads) {
+            const int py = i / Wp, px = i - py * Wp;
+            dst[py * PITCH + px] = __ldg(src + (size_t)clampi(py - kHalo, 0, H - 1) * W + clampi(px - kHalo, 0, W - 1));
+        }
+    }
+
+    // tile-major weights of this image: tile t holds [P/4][32][32] float4
+    auto weight_ptr = [&](int t) -> const float4* {
+        return reinterpret_cast<const float4*>(wts) + ((size_t)b * n_tiles + t) * (P / 4 * kTile * kTile) + ty * kTile + tx;
+    };
+    float w[kPx][P];
+    {
+        const float4* wp = weight_ptr(0);
+#pragma unroll
+        for (int g = 0; g < P / 4; ++g)
+#pragma unroll
+            for (int i = 0; i < kPx; ++i) {
+                const float4 v = __ldg(wp + g * (kTile * kTile) + i * kRowGap * kTile);
+                w[i][4 * g + 0] = v.x;
+                w[i][4 * g + 1] = v.y;
+                w[i][4 * g + 2] = v.z;
+                w[i][4 * g + 3] = v.w;
+            }
+    }
+    __syncthreads();
+
+    float acc[kPx];
+    for (int it = 0; it < num_iter; ++it) {
+        const int cur = it & 1, nxt = cur ^ 1;
+        const bool last_it = (it == num_iter - 1);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int tyi = t / tiles_x;
+            const int y0 = tyi * kTile, x0 = (t - tyi * tiles_x) * kTile;
+            const int sbase = (y0 + ty + kHalo) * PITCH + (x0 + tx + kHalo);
+            const int x = x0 + tx;
+            unsigned valid = 0u;
+#pragma unroll
+            for (int i = 0; i < kPx; ++i)
+                if (x < W && y0 + ty + i * kRowGap < H) valid |= 1u << i;
+            // weights of the tile that follows (this iteration's next tile, or tile 0 of the next iteration)
+            const int tn = (t + 1 == n_tiles) ? 0 : t + 1;
+            const bool more = (n_tiles > 1) && !(last_it && t + 1 == n_tiles);
+            for (int c = 0; c < nc; ++c) {
+                const float* sp = plane(c, cur) + sbase;
+                if (more && c == nc - 1)
+                    sweep_class<D, DS, true, PITCH>(w, sp, dil, weight_ptr(tn), acc);
+                else
+                    sweep_class<D, DS, false, PITCH>(w, sp, dil, nullptr, acc);
+                if (last_it) {
+                    float* o = mask_out + ((size_t)b * C + c0 + c) * HW + (size_t)(y0 + ty) * W + x;
+#pragma unroll
+                    for (int i = 0; i < kPx; ++i)
+                        if ((valid >> i) & 1u) o[(size_t)(i * kRowGap) * W] = acc[i];
+                } else {
+                    float* o = plane(c, nxt) + sbase;
+#pragma unroll
+                    for (int i = 0; i < kPx; ++i)
+                        if ((valid >> i) & 1u) o[i * kRowGap * PITCH] = acc[i];
+                }
+            }
+        }
+        if (last_it) break;
+        __syncthreads();  // interiors of the new planes complete
+        // replicate frame of the new planes (wss/modules.py:57 for the next iteration): frame cells
+        // read interior cells only, so no ordering between threads is needed
+        for (int c = 0; c < nc; ++c) {
+            float* pl = plane(c, nxt);
+            // rows above and below the image: full padded width
+            for (int i = tid; i < 2 * kHalo * Wp; i += kSweepThreads) {
+                const int r = i / Wp, px = i - r * Wp;
+                const int py = (r < kHalo) ? r : (H + r);
+                const int sy = (r < kHalo) ? kHalo : (H + kHalo - 1);
+                pl[py * PITCH + px] = pl[sy * PITCH + clampi(px, kHalo, W + kHalo - 1)];
+            }
+            // left and right bands of the image rows
+            for (int i = tid; i < H * 2 * kHalo; i += kSweepThreads) {
+                const int r = i / (2 * kHalo), q = i - r * (2 * kHalo);
+                const int py = r + kHalo;
+                const int px = (q < kHalo) ? q : (W + q);
+                const int sx = (q < kHalo) ? kHalo : (W + kHalo - 1);
+                pl[py * PITCH + px] = pl[py * PITCH + sx];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+bool pamr_fused_applicable(int H, int W, const Dilations& dil, int D) {
+    if (D > 6 || H > kFusedMaxDim || W > kFusedMaxDim) return false;
+    for (int i = 0; i < D; ++i)
+        if (dil.d[i] > kHalo) return false;
+    return true;
+}
+
+// classes per CTA: as many CTAs as possible up to one wave of the GPU, then the fewest waves
+static int pick_cpb(int B, int C, int cpb_max) {
+    int best = 1;
+    long long best_cost = -1;
+    for (int cpb = 1; cpb <= cpb_max && cpb <= C; ++cpb) {
+        const long long ctas = (long long)B * ceil_div(C, cpb);
+        const long long cost = ((ctas + kNumSMs - 1) / kNumSMs) * cpb;  // waves x classes per CTA
+        if (best_cost < 0 || cost < best_cost || (cost == best_cost && cpb > best)) {
+            best = cpb;
+            best_cost = cost;
+        }
+    }
+    return best;
+}
+
+template <int D, class DS, int PITCH>
+static int launch_fused_one(const float* w, const float* mi, float* mo, int B, int C, int H, int W, int num_iter,
+                            const Dilations& dil, cudaStream_t s) {
+    auto kern = pamr_fused_kernel<D, DS, PITCH>;
+    constexpr size_t kPlaneBytes = (size_t)PITCH * PITCH * 4;
+    constexpr int kCpbMax = (int)((227 * 1024) / (2 * kPlaneBytes));
+    static_assert(kCpbMax >= 1, "plane too large for shared memory");
+    const int cpb = pick_cpb(B, C, kCpbMax);
+    const size_t smem = (size_t)cpb * 2 * kPlaneBytes;
+    static size_t attr_smem = 0;  // per instantiation
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("pamr_fused: smem attribute: %s", cudaGetErrorString(e));
+            return CL4_ECUDA;
+        }
+        attr_smem = smem;
+    }
+    dim3 grid(ceil_div(C, cpb), B);
+    kern<<<grid, kSweepThreads, smem, s>>>(w, mi, mo, C, H, W, cpb, num_iter, dil);
+    return check_launch("pamr_fused");
+}
+
+template <int D, int PITCH>
+static int launch_fused_D(const float* w, const float* mi, float* mo, int B, int C, int H, int W, int num_iter,
+                          const Dilations& dil, cudaStream_t s) {
+    bool voc6 = (D == 6), voc5 = (D == 5);
+    for (int i = 0; i < D && i < 6; ++i) {
+        voc6 = voc6 && dil.d[i] == DilVoc6::get(i);
+        voc5 = voc5 && dil.d[i] == DilVoc5::get(i);
+    }
+    if (D == 6 && voc6) return launch_fused_one<6, DilVoc6, PITCH>(w, mi, mo, B, C, H, W, num_iter, dil, s);
+    if (D == 5 && voc5) return launch_fused_one<5, DilVoc5, PITCH>(w, mi, mo, B, C, H, W, num_iter, dil, s);
+    return launch_fused_one<D, DilRuntime, PITCH>(w, mi, mo, B, C, H, W, num_iter, dil, s);
+}
+
+template <int PITCH>
+static int launch_fused_P(const float* w, const float* mi, float* mo, int B, int C, int H, int W, int num_iter,
+                          const Dilations& dil, int D, cudaStream_t s) {
+    switch (D) {
+        case 1: return launch_fused_D<1, PITCH>(w, mi, mo, B, C, H, W, num_iter, dil, s);
+        case 2: return launch_fused_D<2, PITCH>(w, mi, mo, B, C, H, W, num_iter, dil, s);
+        case 3: return launch_fused_D<3, PITCH>(w, mi, mo, B, C, H, W, num_iter, dil, s);
+        case 4: return launch_fused_D<4, PITCH>(w, mi, mo, B, C, H, W, num_iter, dil, s);
+        case 5: return launch_fused_D<5, PITCH>(w, mi, mo, B, C, H, W, num_iter, dil, s);
+        case 6: return launch_fused_D<6, PITCH>(w, mi, mo, B, C, H, W, num_iter, dil, s);
+    }
+    set_error("pamr_fused: bad D=%d", D);
+    return CL4_EUNSUPPORTED;
+}
+
+// w: tile-major weights; mask_in / mask_out: plain [B*C][H][W]; num_iter >= 1
+int launch_pamr_fused(const float* w, const float* mask_in, float* mask_out, int B, int C, int H, int W, int num_iter,
+                      const Dilations& dil, int D, cudaStream_t s) {
+    if (H <= kTile && W <= kTile) return launch_fused_P<kBox>(w, mask_in, mask_out, B, C, H, W, num_iter, dil, D, s);
+    return launch_fused_P<2 * kTile + 2 * kHalo>(w, mask_in, mask_out, B, C, H, W, num_iter, dil, D, s);
+}
+
+}  // namespace cl4

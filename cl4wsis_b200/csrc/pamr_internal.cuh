@@ -22,4 +22,10 @@ int launch_weights_tma(const float* padded_img, float* w, int B, int K, int H, i
 int launch_sweep_tma(const float* w, const float* padded_in, float* out, int out_padded, int B, int C, int H, int W,
                      const Dilations& dil, int D, cudaStream_t s);
 
+// All iterations on-chip for maps up to 64 x 64 (pamr_fused.cu): D <= 6, every dilation <= 24.
+// w: tile-major weights; mask_in / mask_out: plain [B*C][H][W]; num_iter >= 1.
+bool pamr_fused_applicable(int H, int W, const Dilations& dil, int D);
+int launch_pamr_fused(const float* w, const float* mask_in, float* mask_out, int B, int C, int H, int W, int num_iter,
+                      const Dilations& dil, int D, cudaStream_t s);
+
 }  // namespace cl4

@@ -94,6 +94,36 @@ def test_pamr_oracle_random(cl4, oracle, B, C, H, W, dil, T):
     np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("path", ["fused", "tma", "v1"])
+@pytest.mark.parametrize("B,C,H,W,dil,T", [
+    (16, 21, 32, 32, [1, 2, 4, 8, 12], 10),      # VOC phase-1 call: train.py:81, :379 at crop 512 / stride 16
+    (2, 81, 56, 56, [1, 2, 4, 8, 12], 10),       # coco-voc feature resolution: 4 tiles, weight reload on-chip
+    (3, 5, 64, 64, [1, 2, 4, 8, 12, 24], 7),     # largest fused map, odd iteration count
+    (2, 4, 33, 20, [1, 2, 4, 8, 12, 24], 2),     # two tile rows, one column, W % 4 == 0
+    (1, 3, 40, 36, [2, 5, 24], 3),               # runtime dilation offsets
+    (1, 2, 32, 64, [1, 2, 4, 8, 12, 24], 1),     # single iteration: straight to the output
+])
+def test_pamr_small_map_paths_agree(cl4, oracle, monkeypatch, path, B, C, H, W, dil, T):
+    """The three sweep implementations (all iterations on-chip / TMA-staged / register-L1) on the
+    small maps the trainer really feeds PAMR, each against the oracle."""
+    if path != "fused":
+        monkeypatch.setenv("CL4_SWEEP", path)
+    rng = np.random.default_rng(B + 10 * C + 100 * H + W)
+    x = (rng.integers(0, 256, (B, 3, H, W)) / 255.0).astype(np.float32)
+    m = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).softmax(1).numpy()
+    got = cl4.PAMR(T, dil).cuda()(cuda(x), cuda(m)).cpu().numpy()
+    np.testing.assert_allclose(got, oracle.pamr(x, m, T, dil), rtol=RTOL, atol=ATOL)
+
+
+def test_pamr_fused_odd_width_and_resize(cl4, oracle):
+    """The fused path has no W % 4 requirement and composes with the bilinear resize of :134."""
+    rng = np.random.default_rng(11)
+    x = rng.random((2, 3, 29, 37)).astype(np.float32)
+    m = torch.from_numpy(rng.standard_normal((2, 6, 8, 10)).astype(np.float32)).softmax(1).numpy()
+    got = cl4.PAMR(10, [1, 2, 4, 8, 12]).cuda()(cuda(x), cuda(m)).cpu().numpy()
+    np.testing.assert_allclose(got, oracle.pamr(x, m, 10, [1, 2, 4, 8, 12]), rtol=RTOL, atol=ATOL)
+
+
 def test_pamr_weights_and_single_sweep(cl4, oracle, golden):
     """The two kernels separately, through the C ABI."""
     lib, L = cl4._lib.load(), cl4._lib
