@@ -7,6 +7,8 @@ Drop-in mirrors of the reference API for this path (same names and signatures):
     cl4wsis_b200.modules.utils.find_instance_center        modules/utils.py:463-502
     cl4wsis_b200.modules.utils.group_pixels                modules/utils.py:505-542
     cl4wsis_b200.modules.utils.get_instance_segmentation   modules/utils.py:545-606
+    cl4wsis_b200.modules.utils.refine_label_generation     modules/utils.py:257-385
+    cl4wsis_b200.wss.modules.LocalAffinity[Abs|Copy], LocalStDev   wss/modules.py:17-119
 
 All compute happens in hand-written CUDA kernels behind the C ABI in
 ``include/cl4wsis_b200.h`` (``libcl4wsis_b200.so``); there is no CPU or PyTorch fallback.
@@ -14,7 +16,8 @@ All compute happens in hand-written CUDA kernels behind the C ABI in
 from . import _lib  # noqa: F401
 from .wss.modules import PAMR  # noqa: F401
 from .wss.utils import peak_extract  # noqa: F401
-from .modules.utils import find_instance_center, get_instance_segmentation, group_pixels  # noqa: F401
+from .modules.utils import (find_instance_center, get_instance_segmentation, group_pixels,  # noqa: F401
+                            refine_label_generation)
 from .pipeline import HostPseudoLabelPipeline, PseudoLabelStep  # noqa: F401
 
 __version__ = "0.1.0"
@@ -35,3 +38,4 @@ def patch_reference(wss_modules=None, wss_utils=None, modules_utils=None):
         modules_utils.find_instance_center = mu.find_instance_center
         modules_utils.group_pixels = mu.group_pixels
         modules_utils.get_instance_segmentation = mu.get_instance_segmentation
+        modules_utils.refine_label_generation = mu.refine_label_generation

@@ -40,6 +40,11 @@ SIGNATURES = {
     "cl4_center_nms": (_int, [_vp, _flt, _flt, _int, _int, _int, _int, _vp, _vp, _int, _vp, _sz, _vp]),
     "cl4_ccl4_scratch_bytes": (_sz, [_int, _int]),
     "cl4_ccl4_components": (_int, [_vp, _vp, _flt, _flt, _flt, _int, _int, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
+    "cl4_refine_max_contours": (_int, []),
+    "cl4_refine_scratch_bytes": (_sz, [_int] * 3),
+    "cl4_contours8": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cl4_refine_labels": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, ctypes.c_double, _int, _flt, _int, _int,
+                                 ctypes.c_longlong, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _sz, _vp]),
     "cl4_group_pixels": (_int, [_vp, _vp, _int, _int, _vp, _vp, _vp, _int, _int, _int, _int, _vp]),
 }
 

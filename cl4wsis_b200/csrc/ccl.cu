@@ -5,37 +5,10 @@
 // Union-find over pixels (atomicMin on parent links); a component is represented by its smallest
 // pixel index, which is also OpenCV's label order for 4-connectivity (labels are numbered by the
 // first pixel met in raster order — pinned against cv2 in tests/test_cluster.py).
+#include "ccl.cuh"
 #include "common.cuh"
 
 namespace cl4 {
-
-__device__ __forceinline__ int ccl_find(const int* __restrict__ L, int i) {
-    int p = L[i];
-    while (p != i) {
-        i = p;
-        p = L[i];
-    }
-    return i;
-}
-
-__device__ __forceinline__ void ccl_union(int* L, int a, int b) {
-    bool done;
-    do {
-        a = ccl_find(L, a);
-        b = ccl_find(L, b);
-        if (a < b) {
-            const int old = atomicMin(&L[b], a);
-            done = (old == b);
-            b = old;
-        } else if (b < a) {
-            const int old = atomicMin(&L[a], b);
-            done = (old == a);
-            a = old;
-        } else {
-            done = true;
-        }
-    } while (!done);
-}
 
 // label[i] = i for weak-offset foreground pixels, -1 elsewhere
 __global__ void ccl_init_kernel(const float* __restrict__ off, const unsigned char* __restrict__ fg, float thresh,

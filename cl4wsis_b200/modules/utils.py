@@ -134,3 +134,169 @@ def get_instance_segmentation(fg, ctr_hmp, offsets, threshold=0.1, nms_kernel=3,
             return fg.long()
 
     return _group(new_ctr, offsets, fg)
+
+
+# ------------------------------------------------------------------------------------------------
+# refine_label_generation — modules/utils.py:257-385 (the phase-2 caller, train.py:492-500)
+# ------------------------------------------------------------------------------------------------
+MINIMUM_MASK_SIZE = 20   # modules/utils.py:14 (the validation twin dataset/utils.py:147 uses 50)
+MAXIMUM_NUM_INST = 5     # modules/utils.py:15
+
+_GAUSS_CACHE = {}
+
+
+def gaussian(sigma=6):
+    """The (6*sigma+3)^2 float64 bump of modules/utils.py:49-59 (numpy, as in the reference)."""
+    import numpy as np
+    size = 6 * sigma + 3
+    x = np.arange(0, size, 1, float)
+    y = x[:, np.newaxis]
+    x0, y0 = 3 * sigma + 1, 3 * sigma + 1
+    return np.exp(-((x - x0) ** 2 + (y - y0) ** 2) / (2 * sigma ** 2))
+
+
+def _gauss_f32(sigma, device):
+    key = (sigma, str(device))
+    if key not in _GAUSS_CACHE:
+        # the reference max-combines the float64 bump into a float32 map: same as using float32(bump)
+        _GAUSS_CACHE[key] = torch.from_numpy(gaussian(sigma).astype("float32")).to(device).contiguous()
+    return _GAUSS_CACHE[key]
+
+
+def _refine_inputs(seg_map, center_map, offset_map, label, gt_seg_map):
+    for t, name in ((seg_map, "seg_map"), (center_map, "center_map"), (offset_map, "offset_map"),
+                    (gt_seg_map, "gt_seg_map")):
+        _lib.require_cuda(t, name)
+    dev = center_map.device
+    f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+    return f32(seg_map), f32(center_map), f32(offset_map), f32(label), gt_seg_map.detach().to(dev).long().contiguous()
+
+
+def refine_label_generation_device(seg_map, center_map, offset_map, label, gt_seg_map, top_k, args):
+    """The whole batch in one sequence of kernels (``cl4_refine_labels``), no host round trip.
+    Returns (dict(center, offset, weight), status) where ``status`` is a device int32 tensor: non-zero
+    means a capacity limit was hit and the result must be recomputed with the per-contour path."""
+    lib = _lib.load()
+    seg, ctr, off, lab, gt = _refine_inputs(seg_map, center_map, offset_map, label, gt_seg_map)
+    B, C, H, W = ctr.shape
+    if seg.shape != (B, C + 1, H, W) or off.shape != (B, 2, H, W) or lab.shape != (B, C) or gt.shape != (B, H, W):
+        raise ValueError("refine_label_generation: seg [B,C+1,H,W], center [B,C,H,W], offset [B,2,H,W], "
+                         "label [B,C], gt_seg [B,H,W] expected")
+    dev = ctr.device
+    sigma = int(args.sigma)
+    if sigma != args.sigma:
+        raise NotImplementedError("refine_label_generation: integer sigma only (argparser.py:221)")
+    with torch.cuda.device(dev):
+        out_c = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+        out_o = torch.empty((B, 2, H, W), dtype=torch.float32, device=dev)
+        out_w = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        if B:
+            nbytes = lib.cl4_refine_scratch_bytes(B, H, W)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            g = _gauss_f32(sigma, dev)
+            _lib.check(lib.cl4_refine_labels(
+                _lib.ptr(seg), _lib.ptr(ctr), _lib.ptr(off), _lib.ptr(lab), _lib.ptr(gt), _lib.ptr(g), sigma,
+                float(args.refine_thresh), int(args.kernel), float(args.beta), MINIMUM_MASK_SIZE, MAXIMUM_NUM_INST,
+                -1 if top_k is None else int(top_k), _lib.ptr(out_c), _lib.ptr(out_o), _lib.ptr(out_w),
+                _lib.ptr(status), B, C, H, W, _lib.ptr(scratch), nbytes, _lib.stream_ptr(dev)), "refine_label_generation")
+    return {'center': out_c, 'offset': out_o, 'weight': out_w}, status
+
+
+def contours8(gt_seg_map, label, min_area=MINIMUM_MASK_SIZE):
+    """8-connected contours of every valid (image, class) on the GPU (``cl4_contours8``):
+    -> (comp [B,H,W] int32 slot map, info [B,n_max,5] int32 (first pixel, cls, cx, cy, area), ncomp [B])."""
+    lib = _lib.load()
+    _lib.require_cuda(gt_seg_map, "gt_seg_map")
+    dev = gt_seg_map.device
+    gt = gt_seg_map.detach().long().contiguous()
+    lab = label.detach().to(device=dev, dtype=torch.float32).contiguous()
+    B, H, W = gt.shape
+    C = lab.shape[1]
+    nmax = lib.cl4_refine_max_contours()
+    with torch.cuda.device(dev):
+        comp = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+        info = torch.zeros((B, nmax, 5), dtype=torch.int32, device=dev)
+        ncomp = torch.zeros(B, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        if B:
+            nbytes = lib.cl4_refine_scratch_bytes(B, H, W)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.cl4_contours8(_lib.ptr(gt), _lib.ptr(lab), int(min_area), B, C, H, W, _lib.ptr(comp),
+                                         _lib.ptr(info), _lib.ptr(ncomp), _lib.ptr(status), _lib.ptr(scratch), nbytes,
+                                         _lib.stream_ptr(dev)), "contours8")
+    if int(status.item()) != 0:
+        raise NotImplementedError(f"contours8: more than {nmax} contours of >= {min_area} px in one image")
+    return comp, info, ncomp
+
+
+def refine_label_generation_per_contour(seg_map, center_map, offset_map, label, gt_seg_map, top_k, args):
+    """The reference's loop structure (image x contour x instance, modules/utils.py:295-377) on this
+    package's kernels: exact for every input, at the reference's cost of several host round trips per
+    contour.  Used when the batched path reports a capacity overflow."""
+    seg, ctr, off, lab, gt = _refine_inputs(seg_map, center_map, offset_map, label, gt_seg_map)
+    B, C, H, W = ctr.shape
+    dev = ctr.device
+    prob = torch.softmax(seg, dim=1)
+    prob[:, 1:] *= lab[:, :, None, None]
+    out_c = torch.zeros((B, C, H, W), dtype=torch.float32, device=dev)
+    out_o = torch.zeros((B, 2, H, W), dtype=torch.float32, device=dev)
+    out_w = torch.zeros((B, 1, H, W), dtype=torch.float32, device=dev)
+    yy = torch.arange(H, dtype=torch.float32, device=dev).view(H, 1).expand(H, W)
+    xx = torch.arange(W, dtype=torch.float32, device=dev).view(1, W).expand(H, W)
+    sigma = args.sigma
+    g = _gauss_f32(int(sigma), dev)
+    comp, info, ncomp = contours8(gt, lab)
+    info_h, ncomp_h = info.cpu().numpy(), ncomp.cpu().numpy()
+    for b in range(B):
+        for s in range(int(ncomp_h[b])):
+            _, cls, cx, cy, _ = (int(v) for v in info_h[b, s])
+            contour = comp[b] == s
+            heat = ctr[b, cls] * contour
+            ins = get_instance_segmentation(contour[None], heat[None, None], off[b][None],
+                                            threshold=args.refine_thresh, nms_kernel=args.kernel, ignore=True,
+                                            beta=args.beta, top_k=top_k).squeeze(0)
+            n_ins = int(ins.max())
+            if n_ins > MAXIMUM_NUM_INST:
+                continue
+            for i in range(1, n_ins + 1):
+                index = torch.where(ins == i)
+                if index[0].numel() == 0:
+                    continue
+                pmax = heat[index].argmax()
+                seg_score = prob[b, cls + 1][index].mean().item()
+                py, px = index[0][pmax].item(), index[1][pmax].item()
+                center_score = heat[py, px].item()
+                if center_score < args.refine_thresh:
+                    py, px = cy, cx
+                    conf = seg_score
+                else:
+                    conf = center_score * seg_score
+                conf = max(0, min(conf, 1))
+                # gaussian max-splat (center_map_gen, modules/utils.py:84-119)
+                x0, y0 = int(round(px - 3 * sigma - 1)), int(round(py - 3 * sigma - 1))
+                x1, y1 = int(round(px + 3 * sigma + 2)), int(round(py + 3 * sigma + 2))
+                ix0, ix1, iy0, iy1 = max(0, x0), min(x1, W), max(0, y0), min(y1, H)
+                out_c[b, cls, iy0:iy1, ix0:ix1] = torch.maximum(out_c[b, cls, iy0:iy1, ix0:ix1],
+                                                                g[iy0 - y0:iy1 - y0, ix0 - x0:ix1 - x0])
+                out_w[b, 0][index] = conf
+                out_o[b, 0][index] = py - yy[index]
+                out_o[b, 1][index] = px - xx[index]
+    return {'center': out_c, 'offset': out_o, 'weight': out_w}
+
+
+def refine_label_generation(seg_map, center_map, offset_map, label, gt_seg_map, top_k, args):
+    """Refined-label generation (Self-Refinement) with image-level labels — modules/utils.py:257-385.
+
+    seg_map [B,C+1,H,W] logits, center_map [B,C,H,W], offset_map [B,2,H,W], label [B,C] one-hot,
+    gt_seg_map [B,H,W] labels, ``args`` with ``refine_thresh``, ``kernel``, ``beta``, ``sigma``
+    -> {'center': [B,C,H,W], 'offset': [B,2,H,W], 'weight': [B,1,H,W]} float32 on the inputs' device.
+
+    Runs the whole batch on the device with ONE host synchronisation (the status word); the
+    reference needs >= 6 per contour.  Inputs that exceed a capacity limit of the
+    batched path (status != 0) are recomputed by the exact per-contour path.
+    """
+    out, status = refine_label_generation_device(seg_map, center_map, offset_map, label, gt_seg_map, top_k, args)
+    if int(status.item()) != 0:
+        return refine_label_generation_per_contour(seg_map, center_map, offset_map, label, gt_seg_map, top_k, args)
+    return out

@@ -151,6 +151,41 @@ int cl4_ccl4_components(const float* offsets, const unsigned char* fg, float thr
                         int H, int W, long long* roots_out, long long* stats_out, int* count_out, int max_out,
                         void* scratch, size_t scratch_bytes, cl4_stream_t stream);
 
+/* ------------------------------------------------------------------------- *
+ * refine_label_generation — modules/utils.py:257-385, the phase-2 caller of the
+ * post-processing (train.py:492-500), for a whole batch with no host round trip.
+ *
+ * cl4_contours8: the cv2.connectedComponentsWithStats(seg == cls+1, connectivity=8)
+ * of :305-307 for every (image, valid class) at once.  gt_seg [B,H,W] int64 labels
+ * (0 = background, cls+1 otherwise), label [B,C] (non-zero = class present, :299).
+ * comp_out [B,H,W] int32: contour slot of each pixel, -1 for background, invalid
+ * classes and contours smaller than min_area (:313); info_out
+ * [B,cl4_refine_max_contours(),5] int32 per slot: first pixel index, class,
+ * int(centroid x), int(centroid y), area; ncomp_out [B]; status_out [1] (bit 0:
+ * more contours than slots).  Slots are numbered in no particular order (the
+ * reference's results do not depend on OpenCV's label order).
+ *
+ * cl4_refine_labels: seg_logits [B,C+1,H,W], center [B,C,H,W], offsets [B,2,H,W]
+ * -> out_center [B,C,H,W], out_offset [B,2,H,W], out_weight [B,1,H,W] (all fp32).
+ * gauss: the (6*sigma+3)^2 bump of modules/utils.py:49-59 as fp32; refine_thresh,
+ * nms_kernel, beta, sigma = args.refine_thresh / kernel / beta / sigma; min_area =
+ * MINIMUM_MASK_SIZE (20), max_inst = MAXIMUM_NUM_INST (5); top_k < 0 = None.
+ * status_out [1] device int32: 0 = done; any bit set = a capacity limit was hit
+ * (1: > 1024 contours per image, 2: > 64 centres in a contour, 4: > 4096 centres or
+ * cluster components per image, 8: the reference's degenerate top_k branch would
+ * run) and the outputs must be recomputed contour by contour.
+ * ------------------------------------------------------------------------- */
+int cl4_refine_max_contours(void);
+size_t cl4_refine_scratch_bytes(int B, int H, int W);
+int cl4_contours8(const long long* gt_seg, const float* label, int min_area, int B, int C, int H, int W,
+                  int* comp_out, int* info_out, int* ncomp_out, int* status_out, void* scratch,
+                  size_t scratch_bytes, cl4_stream_t stream);
+int cl4_refine_labels(const float* seg_logits, const float* center, const float* offsets, const float* label,
+                      const long long* gt_seg, const float* gauss, int sigma, double refine_thresh,
+                      int nms_kernel, float beta, int min_area, int max_inst, long long top_k,
+                      float* out_center, float* out_offset, float* out_weight, int* status_out, int B, int C,
+                      int H, int W, void* scratch, size_t scratch_bytes, cl4_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

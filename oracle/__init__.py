@@ -8,3 +8,4 @@ from .oracle import (  # noqa: F401
     build, pamr, pamr_weights, local_affinity, local_stdev, peak_extract, find_instance_center, group_pixels,
     get_instance_segmentation, cluster_peaks, resize_bilinear_ac, num_threads, set_num_threads,
 )
+from . import labelgen  # noqa: F401,E402  (numpy/OpenCV restatement of the callers: smoothing, label generation)

@@ -365,3 +365,100 @@ def test_pseudo_label_step_matches_per_image_oracle(cl4, oracle):
             assert int(ids[b].abs().sum()) == 0  # ignore=True: zeros (modules/utils.py:597-598)
         else:
             assert np.array_equal(ids[b].cpu().numpy(), oracle.group_pixels(ctr, off[b:b + 1])[0])
+
+
+# --------------------------------------------------------------------------- refine_label_generation
+class _Args:
+    def __init__(self, refine_thresh, kernel, beta, sigma):
+        self.refine_thresh, self.kernel, self.beta, self.sigma = refine_thresh, kernel, beta, sigma
+
+
+def _refine_case(g, ci):
+    k = f"refine_{ci}__"
+    thr, kernel, beta, sigma, topk = g[k + "args"]
+    args = _Args(float(thr), int(kernel), float(beta), int(sigma))
+    ins = [cuda(g[k + n]) for n in ("seg", "heat", "off", "label", "gt")]
+    return k, ins, (None if topk < 0 else int(topk)), args
+
+
+def _check_refine(r, g, k):
+    assert np.array_equal(r["center"].cpu().numpy(), g[k + "center"])
+    assert np.array_equal(r["offset"].cpu().numpy(), g[k + "offset"])
+    w = r["weight"].cpu().numpy()
+    assert np.array_equal(w > 0, g[k + "weight"] > 0)
+    np.testing.assert_allclose(w, g[k + "weight"], rtol=2e-6, atol=0)
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2, 3])
+def test_refine_label_generation_golden(cl4, golden_more, ci):
+    """Batched device path against the reference's outputs: centre splats and offsets bit-exact,
+    confidences to fp32 rounding."""
+    from cl4wsis_b200.modules import utils as mu
+    g = golden_more("refine")
+    k, ins, topk, args = _refine_case(g, ci)
+    r, status = mu.refine_label_generation_device(*ins, topk, args)
+    if ci == 2:  # noisy heat + 5x5 NMS: > 64 centres in one contour -> status bit 1 -> per-contour path
+        assert int(status.item()) == 2
+    else:
+        assert int(status.item()) == 0
+        _check_refine(r, g, k)
+    _check_refine(mu.refine_label_generation(*ins, topk, args), g, k)
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2, 3])
+def test_refine_label_generation_per_contour_golden(cl4, golden_more, ci):
+    """The exact per-contour path (used on overflow) against the same fixtures."""
+    from cl4wsis_b200.modules import utils as mu
+    g = golden_more("refine")
+    k, ins, topk, args = _refine_case(g, ci)
+    _check_refine(mu.refine_label_generation_per_contour(*ins, topk, args), g, k)
+
+
+def test_refine_label_generation_overflow_falls_back(cl4, golden_more):
+    """A degenerate top_k (>= centres of a contour) trips the status word; the drop-in then answers
+    through the per-contour path, which reproduces the reference's degenerate branch."""
+    from cl4wsis_b200.modules import utils as mu
+    g = golden_more("refine")
+    k, ins, _, args = _refine_case(g, 0)
+    _, status = mu.refine_label_generation_device(*ins, 1, args)
+    assert int(status.item()) & 8
+    with redirect_stdout(io.StringIO()):
+        a = mu.refine_label_generation(*ins, 1, args)
+        b = mu.refine_label_generation_per_contour(*ins, 1, args)
+    for key in ("center", "offset", "weight"):
+        assert torch.equal(a[key], b[key])
+
+
+def test_refine_label_generation_random_vs_oracle(cl4, oracle):
+    """Larger random scenes (512x512, 20 classes): device path against the numpy/OpenCV oracle."""
+    from cl4wsis_b200.modules import utils as mu
+    rng = np.random.default_rng(77)
+    B, C, H, W = 2, 20, 512, 512
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    seg = rng.standard_normal((B, C + 1, H, W)).astype(np.float32)
+    heat = (0.05 * rng.random((B, C, H, W))).astype(np.float32)
+    off = (0.3 * rng.standard_normal((B, 2, H, W)) + 40).astype(np.float32)
+    gt = np.zeros((B, H, W), np.int64)
+    lab = np.zeros((B, C), np.float32)
+    for b in range(B):
+        for _ in range(14):
+            cls = int(rng.integers(0, C)); cy, cx = int(rng.integers(20, H - 20)), int(rng.integers(20, W - 20))
+            ry, rx = int(rng.integers(4, 60)), int(rng.integers(4, 60))
+            m = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1
+            gt[b][m] = cls + 1
+            if rng.random() < 0.85:
+                lab[b, cls] = 1
+            if rng.random() < 0.8:
+                heat[b, cls] = np.maximum(heat[b, cls], rng.uniform(0.25, 0.95) * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / 72).astype(np.float32))
+            off[b, 0][m] = (cy - yy)[m] + 0.3 * rng.standard_normal(int(m.sum()))
+            off[b, 1][m] = (cx - xx)[m] + 0.3 * rng.standard_normal(int(m.sum()))
+        for c in range(C + 1):
+            seg[b, c][gt[b] == c] += 3
+    args = _Args(0.3, 41, 3.0, 6)
+    want = oracle.labelgen.refine_label_generation(seg, heat, off, lab, gt, 10000, refine_thresh=0.3, kernel=41, beta=3.0, sigma=6)
+    r, status = mu.refine_label_generation_device(cuda(seg), cuda(heat), cuda(off), cuda(lab), cuda(gt), 10000, args)
+    assert int(status.item()) == 0
+    assert (want["weight"] > 0).sum() > 10000
+    assert np.array_equal(r["center"].cpu().numpy(), want["center"])
+    assert np.array_equal(r["offset"].cpu().numpy(), want["offset"])
+    np.testing.assert_allclose(r["weight"].cpu().numpy(), want["weight"], rtol=2e-6, atol=0)

@@ -124,3 +124,40 @@ def test_helper_stencils_match_reference(golden_more, oracle, name):
         assert got.shape == g[f"{name}__{key}"].shape
         assert np.array_equal(got, g[f"{name}__{key}"]), (name, key)
     np.testing.assert_allclose(oracle.local_stdev(x, dil), g[name + "__std"], rtol=1e-5, atol=1e-7)
+
+
+# --------------------------------------------------------------------------- callers
+def _refine_args(g, ci):
+    thr, kernel, beta, sigma, topk = g[f"refine_{ci}__args"]
+    return dict(refine_thresh=float(thr), kernel=int(kernel), beta=float(beta), sigma=int(sigma)), (None if topk < 0 else int(topk))
+
+
+def test_refine_label_generation_matches_reference(golden_more, oracle):
+    """modules/utils.py:257-385: centre splats and offsets bit-exact, confidences to fp32 rounding
+    (the reference's mean over the instance mask is a float reduction)."""
+    g = golden_more("refine")
+    for ci in range(int(g["n"])):
+        k = f"refine_{ci}__"
+        kw, topk = _refine_args(g, ci)
+        r = oracle.labelgen.refine_label_generation(g[k + "seg"], g[k + "heat"], g[k + "off"], g[k + "label"], g[k + "gt"],
+                                                    topk, **kw)
+        assert np.array_equal(r["center"], g[k + "center"]), ci
+        assert np.array_equal(r["offset"], g[k + "offset"]), ci
+        assert np.array_equal(r["weight"] > 0, g[k + "weight"] > 0), ci
+        np.testing.assert_allclose(r["weight"], g[k + "weight"], rtol=2e-6, atol=0)
+    assert (g["refine_0__weight"] > 0).sum() > 1000 and (g["refine_3__weight"] > 0).sum() == 0
+
+
+def test_smoothing_and_pseudo_label_generation_match_reference(golden_more, oracle):
+    g = golden_more("pseudo")
+    for i in range(int(g["smooth__n"])):
+        np.testing.assert_allclose(oracle.labelgen.smoothing(g[f"smooth_{i}__x"]), g[f"smooth_{i}__y"], rtol=1e-6, atol=1e-7)
+    for ci in range(int(g["pseudo__n"])):
+        k = f"pseudo_{ci}__"
+        sigma = int(g[k + "sigma"])
+        gg = oracle.labelgen.gaussian(sigma)
+        assert np.array_equal(gg, g[k + "g"])
+        pts = [[int(x), int(y), int(c), float(cf)] for x, y, c, cf in g[k + "points"]]
+        c, o, w, n = oracle.labelgen.pseudo_label_generation(g[k + "gt"], pts, g[k + "label"], g[k + "center"].shape[0], sigma, gg)
+        assert n == int(g[k + "match"])
+        assert np.array_equal(c, g[k + "center"]) and np.array_equal(o, g[k + "offset"]) and np.array_equal(w, g[k + "weight"])
