@@ -40,6 +40,9 @@ SIGNATURES = {
     "cl4_center_nms": (_int, [_vp, _flt, _flt, _int, _int, _int, _int, _vp, _vp, _int, _vp, _sz, _vp]),
     "cl4_ccl4_scratch_bytes": (_sz, [_int, _int]),
     "cl4_ccl4_components": (_int, [_vp, _vp, _flt, _flt, _flt, _int, _int, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
+    "cl4_smoothing": (_int, [_vp, _vp, _int, _int, _int, _int, _vp]),
+    "cl4_pseudo_labels": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _flt, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp,
+                                 _int, _int, _int, _int, _vp, _sz, _vp]),
     "cl4_refine_max_contours": (_int, []),
     "cl4_refine_scratch_bytes": (_sz, [_int] * 3),
     "cl4_contours8": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -1,5 +1,5 @@
 // Device-resident, batched refine_label_generation (reference modules/utils.py:257-385, the live
-// phase-2 caller of the hot path: train.py:492-500).
+// phase-2 caller of the hot path: train.py:492-500) and pseudo_label_generation (:179-253, train.py:451-466).
 //
 // The reference walks image x class x 8-connected contour on the host; for every contour it copies a
 // mask to the CPU for OpenCV, calls get_instance_segmentation (centre NMS, cluster_peaks via OpenCV,
@@ -581,7 +581,98 @@ static int run_contours(const long long* gt, const float* label, RefDims d, int 
     return check_launch("refine contours");
 }
 
+// ---- pseudo_label_generation (modules/utils.py:179-253) for a batch: contours holding exactly one
+// confident CAM peak of their class become instances centred on the contour's centroid.
+__global__ void pl_match_kernel(const float* __restrict__ conf, const int* __restrict__ py, const int* __restrict__ px,
+                                const float* __restrict__ label, RefDims d, int K, float thresh,
+                                const int* __restrict__ comp_all, RefComp* __restrict__ comps) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (t >= d.C * K) return;
+    const int c = t / K, j = t - c * K;
+    if (label[(size_t)b * d.C + c] == 0.f) return;  // valid_label = np.nonzero(cls_label[b])   train.py:453
+    const float* cf = conf + ((size_t)b * d.C + c) * K;
+    for (int i = 0; i <= j; ++i)
+        if (cf[i] < thresh) return;  // `if conf < pseudo_thresh: break` over the score-sorted peaks  train.py:456-457
+    const size_t o = ((size_t)b * d.C + c) * K + j;
+    const int y = py[o], x = px[o];
+    if (y < 0 || y >= d.H || x < 0 || x >= d.W) return;
+    const int s = comp_all[(size_t)b * d.HW + y * d.W + x];
+    if (s < 0) return;
+    RefComp& cc = comps[(size_t)b * kRefMaxComp + s];
+    if (cc.cls == c) atomicAdd(&cc.n_nms, 1);  // points of this class inside the contour (:235-238)
+}
+
+__global__ void pl_accept_kernel(RefComp* __restrict__ comps, const int* __restrict__ ncomp, int* __restrict__ total_match) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (s >= min(ncomp[b], kRefMaxComp)) return;
+    RefComp& c = comps[(size_t)b * kRefMaxComp + s];
+    if (c.n_nms == 1) {  // accept: 1 contour - 1 point (:241); the centre is the contour's centroid (:245)
+        c.n_ins = 1;
+        c.cnt[1] = 1;
+        c.px[1] = c.cx;
+        c.py[1] = c.cy;
+        c.conf[1] = 1.f;
+        atomicAdd(&total_match[b], 1);
+    } else {
+        c.n_ins = 0;
+    }
+}
+
+__global__ void pl_write_kernel(RefDims d, const int* __restrict__ comp_all, const RefComp* __restrict__ comps,
+                                float* __restrict__ out_offset, float* __restrict__ out_weight) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (i >= d.HW) return;
+    const size_t o = (size_t)b * d.HW;
+    const int s = comp_all[o + i];
+    float w = 0.f, oy = 0.f, ox = 0.f;
+    if (s >= 0) {
+        const RefComp& c = comps[(size_t)b * kRefMaxComp + s];
+        if (c.n_ins == 1) {
+            const int y = i / d.W, x = i - y * d.W;
+            w = 1.f;
+            oy = (float)c.cy - (float)y;  // cy - y_coord[mask_index]  (:250-251)
+            ox = (float)c.cx - (float)x;
+        }
+    }
+    out_weight[o + i] = w;
+    out_offset[(size_t)b * 2 * d.HW + i] = oy;
+    out_offset[(size_t)b * 2 * d.HW + d.HW + i] = ox;
+}
+
 }  // namespace cl4
+
+extern "C" int cl4_pseudo_labels(const long long* seg_gt, const float* cls_label, const float* peak_conf,
+                                 const int* peak_y, const int* peak_x, int K, float pseudo_thresh, const float* gauss,
+                                 int sigma, int min_area, float* out_center, float* out_offset, float* out_weight,
+                                 int* total_match, int* status_out, int B, int C, int H, int W, void* scratch,
+                                 size_t scratch_bytes, cl4_stream_t stream) {
+    using namespace cl4;
+    CL4_REQUIRE(B >= 0 && C >= 1 && H > 0 && W > 0 && (long long)H * W < (1ll << 30), CL4_EINVAL, "pseudo_labels: bad shape");
+    CL4_REQUIRE(B <= 65535, CL4_EUNSUPPORTED, "pseudo_labels: batch > 65535");
+    CL4_REQUIRE(K >= 1 && sigma >= 0, CL4_EINVAL, "pseudo_labels: bad K or sigma");
+    if (B == 0) return CL4_OK;
+    CL4_REQUIRE(seg_gt && cls_label && peak_conf && peak_y && peak_x && gauss && out_center && out_offset && out_weight &&
+                    total_match && status_out, CL4_EINVAL, "pseudo_labels: null pointer");
+    CL4_REQUIRE(scratch && scratch_bytes >= cl4_refine_scratch_bytes(B, H, W), CL4_ESCRATCH, "pseudo_labels: scratch too small");
+    RefDims d{B, C, H, W, H * W};
+    RefScratch sc = ref_layout(reinterpret_cast<char*>(scratch), B, H, W);
+    cudaStream_t s = (cudaStream_t)stream;
+    REF_CUDA(cudaMemsetAsync(out_center, 0, sizeof(float) * (size_t)B * C * d.HW, s), "memset");
+    REF_CUDA(cudaMemsetAsync(total_match, 0, sizeof(int) * (size_t)B, s), "memset");
+    int rc = run_contours(seg_gt, cls_label, d, min_area, sc, s);
+    if (rc != CL4_OK) return rc;
+    dim3 lin(ceil_div(d.HW, 256), B);
+    pl_match_kernel<<<dim3(ceil_div(C * K, 128), B), 128, 0, s>>>(peak_conf, peak_y, peak_x, cls_label, d, K, pseudo_thresh,
+                                                                 sc.comp, sc.comps);
+    pl_accept_kernel<<<dim3(ceil_div(kRefMaxComp, 128), B), 128, 0, s>>>(sc.comps, sc.ncomp, total_match);
+    pl_write_kernel<<<lin, 256, 0, s>>>(d, sc.comp, sc.comps, out_offset, out_weight);
+    ref_splat_kernel<<<dim3(kRefMaxComp, B), 256, 0, s>>>(d, gauss, sigma, 1, sc.comps, sc.ncomp, out_center);
+    REF_CUDA(cudaMemcpyAsync(status_out, sc.status, 4, cudaMemcpyDeviceToDevice, s), "copy");
+    return check_launch("pseudo_labels");
+}
 
 extern "C" int cl4_refine_max_contours(void) { return cl4::kRefMaxComp; }
 

@@ -89,6 +89,20 @@ local_stdev_kernel(const float* __restrict__ in, float* __restrict__ out, int H,
     out[(size_t)blockIdx.z * HW + (size_t)y * W + x] = sqrtf(ss / (float)(N - 1));
 }
 
+// smoothing(heat, kernel) = avg_pool2d(kernel, stride 1, zero padding (k-1)//2, padded cells counted):
+// wss/utils.py:28-32.  Window values are added in row-major order (ATen's order), then divided by k*k.
+__global__ void __launch_bounds__(256)
+smoothing_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int r, float area) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float* pl = in + (size_t)blockIdx.z * H * W;
+    float acc = 0.f;
+    for (int yy = max(y - r, 0); yy <= min(y + r, H - 1); ++yy)
+        for (int xx = max(x - r, 0); xx <= min(x + r, W - 1); ++xx) acc = __fadd_rn(acc, __ldg(pl + (size_t)yy * W + xx));
+    out[(size_t)blockIdx.z * H * W + (size_t)y * W + x] = __fdiv_rn(acc, area);  // sum / divide_factor, as ATen
+}
+
 static int stencil_args(const char* what, long long planes, int H, int W, const int* dilations, int D, Dilations* dil) {
     CL4_REQUIRE(planes >= 0 && H > 0 && W > 0, CL4_EINVAL, "%s: bad shape", what);
     CL4_REQUIRE(planes <= 65535, CL4_EUNSUPPORTED, "%s: more than 65535 planes", what);
@@ -120,6 +134,19 @@ extern "C" int cl4_local_affinity(const float* x, float* out, int planes, int H,
     else if (mode == kAbs) local_affinity_kernel<kAbs><<<grid, 128, 0, s>>>(x, out, H, W, dil, D);
     else local_affinity_kernel<kCopy><<<grid, 128, 0, s>>>(x, out, H, W, dil, D);
     return check_launch("local_affinity");
+}
+
+extern "C" int cl4_smoothing(const float* x, float* out, int planes, int H, int W, int kernel, cl4_stream_t stream) {
+    using namespace cl4;
+    CL4_REQUIRE(planes >= 0 && H > 0 && W > 0, CL4_EINVAL, "smoothing: bad shape");
+    CL4_REQUIRE(planes <= 65535, CL4_EUNSUPPORTED, "smoothing: more than 65535 planes");
+    CL4_REQUIRE(kernel > 0 && (kernel & 1), CL4_EINVAL, "smoothing: kernel must be odd and positive, got %d", kernel);
+    if (planes == 0) return CL4_OK;
+    CL4_REQUIRE(x && out && x != out, CL4_EINVAL, "smoothing: null or aliased pointers");
+    dim3 grid(ceil_div(W, 32), ceil_div(H, 8), planes);
+    smoothing_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, out, H, W, (kernel - 1) / 2,
+                                                                    (float)(kernel * kernel));
+    return check_launch("smoothing");
 }
 
 extern "C" int cl4_local_stdev(const float* x, float* out, int planes, int H, int W, const int* dilations, int D,

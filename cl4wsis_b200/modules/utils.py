@@ -300,3 +300,48 @@ def refine_label_generation(seg_map, center_map, offset_map, label, gt_seg_map, 
     if int(status.item()) != 0:
         return refine_label_generation_per_contour(seg_map, center_map, offset_map, label, gt_seg_map, top_k, args)
     return out
+
+
+def pseudo_label_generation_batch(seg_gt, peaks, cls_label, pseudo_thresh, sigma):
+    """The per-image loop of train.py:451-477 — points from ``peak_extract`` filtered by
+    ``pseudo_thresh``, then ``pseudo_label_generation`` (modules/utils.py:179-253) per image — for the
+    whole batch on the device.
+
+    seg_gt [B,H,W] labels (CUDA), peaks = (conf f32, ys i32, xs i32) each [B,C,K] CUDA tensors as
+    returned by ``cl4wsis_b200.wss.utils.peak_extract_device``, cls_label [B,C] (non-zero = class
+    considered, train.py:446-447) -> (center [B,C,H,W], offset [B,2,H,W], weight [B,1,H,W],
+    total_match [B] int32), float32 on the device: the stacked outputs of the reference loop.
+    """
+    lib = _lib.load()
+    _lib.require_cuda(seg_gt, "seg_gt")
+    conf, ys, xs = peaks
+    dev = seg_gt.device
+    gt = seg_gt.detach().long().contiguous()
+    lab = torch.as_tensor(cls_label).detach().to(device=dev, dtype=torch.float32).contiguous()
+    conf = conf.detach().to(device=dev, dtype=torch.float32).contiguous()
+    ys = ys.detach().to(device=dev, dtype=torch.int32).contiguous()
+    xs = xs.detach().to(device=dev, dtype=torch.int32).contiguous()
+    B, H, W = gt.shape
+    C = lab.shape[1]
+    if conf.shape[:2] != (B, C) or ys.shape != conf.shape or xs.shape != conf.shape:
+        raise ValueError("pseudo_label_generation_batch: peaks must be three [B,C,K] tensors")
+    K = conf.shape[2]
+    sigma = int(sigma)
+    with torch.cuda.device(dev):
+        out_c = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+        out_o = torch.empty((B, 2, H, W), dtype=torch.float32, device=dev)
+        out_w = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+        match = torch.zeros(B, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        if B:
+            nbytes = lib.cl4_refine_scratch_bytes(B, H, W)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.cl4_pseudo_labels(_lib.ptr(gt), _lib.ptr(lab), _lib.ptr(conf), _lib.ptr(ys), _lib.ptr(xs), K,
+                                             float(pseudo_thresh), _lib.ptr(_gauss_f32(sigma, dev)), sigma,
+                                             MINIMUM_MASK_SIZE, _lib.ptr(out_c), _lib.ptr(out_o), _lib.ptr(out_w),
+                                             _lib.ptr(match), _lib.ptr(status), B, C, H, W, _lib.ptr(scratch), nbytes,
+                                             _lib.stream_ptr(dev)), "pseudo_label_generation")
+    if int(status.item()) != 0:
+        raise NotImplementedError(f"pseudo_label_generation_batch: more than {lib.cl4_refine_max_contours()} contours "
+                                  f"of >= {MINIMUM_MASK_SIZE} px in one image")
+    return out_c, out_o, out_w, match

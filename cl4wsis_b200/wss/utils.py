@@ -1,4 +1,4 @@
-"""Drop-in ``peak_extract`` (reference wss/utils.py:3-25) on the sm_100a NMS + top-K kernels."""
+"""Drop-in ``peak_extract`` and ``smoothing`` (reference wss/utils.py:3-32) on sm_100a kernels."""
 import torch
 
 from .. import _lib
@@ -41,3 +41,23 @@ def peak_extract(heat, kernel=5, K=25):
     to torch.topk)."""
     scores, ys, xs = peak_extract_device(heat, kernel, K)
     return scores.cpu().numpy(), ys.cpu().numpy(), xs.cpu().numpy()
+
+
+def smoothing(heat, kernel=3):
+    """wss/utils.py:28-32: k x k average pooling, stride 1, zero padding (padded cells counted).
+    heat [B,C,H,W] (or any [...,H,W]) fp32 CUDA -> same shape."""
+    lib = _lib.load()
+    _lib.require_cuda(heat, "heat")
+    if kernel % 2 == 0:
+        raise NotImplementedError(f"smoothing: even kernel {kernel} shrinks the map in the reference; not supported")
+    x = heat.detach()
+    if x.dtype != torch.float32:
+        x = x.float()
+    x = x.contiguous()
+    H, W = x.shape[-2:]
+    out = torch.empty_like(x)
+    planes = x.numel() // (H * W) if x.numel() else 0
+    with torch.cuda.device(x.device):
+        _lib.check(lib.cl4_smoothing(_lib.ptr(x), _lib.ptr(out), planes, H, W, int(kernel), _lib.stream_ptr(x.device)),
+                   "smoothing")
+    return out

@@ -58,6 +58,11 @@ int cl4_local_affinity(const float* x, float* out, int planes, int H, int W, con
 int cl4_local_stdev(const float* x, float* out, int planes, int H, int W, const int* dilations, int D,
                     cl4_stream_t stream);
 
+/* smoothing(heat, kernel=3) — wss/utils.py:28-32 (applied to the CAM before peak_extract,
+ * train.py:429): avg_pool2d(kernel, stride 1, zero padding (kernel-1)//2, padded cells counted).
+ * x [planes,H,W] -> out [planes,H,W]; kernel odd; out must not alias x. */
+int cl4_smoothing(const float* x, float* out, int planes, int H, int W, int kernel, cl4_stream_t stream);
+
 /* F.interpolate(mask, size=(H,W), mode="bilinear", align_corners=True), the first
  * line of PAMR.forward (wss/modules.py:134).  in [planes,h,w] -> out [planes,H,W]. */
 int cl4_resize_bilinear_ac(const float* in, float* out, int planes, int h, int w, int H, int W,
@@ -176,6 +181,18 @@ int cl4_ccl4_components(const float* offsets, const unsigned char* fg, float thr
  * run) and the outputs must be recomputed contour by contour.
  * ------------------------------------------------------------------------- */
 int cl4_refine_max_contours(void);
+/* pseudo_label_generation — modules/utils.py:179-253 as driven by train.py:451-466, for a batch:
+ * the peaks of wss.utils.peak_extract (peak_conf f32, peak_y/peak_x i32, all [B,C,K], score-sorted)
+ * with conf >= pseudo_thresh are matched to the 8-connected contours of seg_gt [B,H,W]; a contour of
+ * >= min_area pixels holding exactly ONE peak of its class becomes an instance: gaussian max-splat at
+ * the contour's centroid into out_center [B,C,H,W], weight 1 and centroid offsets on its pixels
+ * (out_weight [B,1,H,W], out_offset [B,2,H,W]); total_match [B] int32 counts the accepted contours.
+ * cls_label [B,C]: non-zero = class considered.  Scratch: cl4_refine_scratch_bytes(B,H,W). */
+int cl4_pseudo_labels(const long long* seg_gt, const float* cls_label, const float* peak_conf,
+                      const int* peak_y, const int* peak_x, int K, float pseudo_thresh, const float* gauss,
+                      int sigma, int min_area, float* out_center, float* out_offset, float* out_weight,
+                      int* total_match, int* status_out, int B, int C, int H, int W, void* scratch,
+                      size_t scratch_bytes, cl4_stream_t stream);
 size_t cl4_refine_scratch_bytes(int B, int H, int W);
 int cl4_contours8(const long long* gt_seg, const float* label, int min_area, int B, int C, int H, int W,
                   int* comp_out, int* info_out, int* ncomp_out, int* status_out, void* scratch,

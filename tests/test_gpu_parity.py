@@ -462,3 +462,82 @@ def test_refine_label_generation_random_vs_oracle(cl4, oracle):
     assert np.array_equal(r["center"].cpu().numpy(), want["center"])
     assert np.array_equal(r["offset"].cpu().numpy(), want["offset"])
     np.testing.assert_allclose(r["weight"].cpu().numpy(), want["weight"], rtol=2e-6, atol=0)
+
+
+# --------------------------------------------------------------------------- smoothing / pseudo labels
+def test_smoothing_golden(cl4, golden_more, oracle):
+    from cl4wsis_b200.wss.utils import smoothing
+    g = golden_more("pseudo")
+    for i in range(int(g["smooth__n"])):
+        np.testing.assert_allclose(smoothing(cuda(g[f"smooth_{i}__x"])).cpu().numpy(), g[f"smooth_{i}__y"], rtol=1e-6, atol=1e-7)
+    x = np.random.default_rng(1).random((2, 20, 64, 64)).astype(np.float32)
+    for k in (3, 5):
+        np.testing.assert_allclose(smoothing(cuda(x), k).cpu().numpy(), oracle.labelgen.smoothing(x, k), rtol=1e-6, atol=1e-7)
+
+
+def _peaks_from_points(points, C, K):
+    conf = np.zeros((1, C, K), np.float32); ys = np.zeros((1, C, K), np.int32); xs = np.zeros((1, C, K), np.int32)
+    for c in range(C):
+        pts = sorted([p for p in points if int(p[2]) == c], key=lambda p: -p[3])
+        for j, (x, y, _c, cf) in enumerate(pts):
+            conf[0, c, j], ys[0, c, j], xs[0, c, j] = cf, y, x
+    return conf, ys, xs
+
+
+@pytest.mark.parametrize("ci", [0, 1])
+def test_pseudo_label_generation_golden(cl4, golden_more, ci):
+    """train.py:451-466 + modules/utils.py:179-253 against reference outputs: everything bit-exact."""
+    from cl4wsis_b200.modules.utils import pseudo_label_generation_batch
+    g = golden_more("pseudo")
+    k = f"pseudo_{ci}__"
+    C = g[k + "center"].shape[0]
+    conf, ys, xs = _peaks_from_points(g[k + "points"].tolist(), C, 4)
+    c, o, w, m = pseudo_label_generation_batch(cuda(g[k + "gt"][None]), (cuda(conf), cuda(ys), cuda(xs)),
+                                               cuda(g[k + "label"][None]), 0.7, int(g[k + "sigma"]))
+    assert int(m[0]) == int(g[k + "match"])
+    assert np.array_equal(c[0].cpu().numpy(), g[k + "center"])
+    assert np.array_equal(o[0].cpu().numpy(), g[k + "offset"])
+    assert np.array_equal(w[0].cpu().numpy(), g[k + "weight"])
+
+
+def test_phase2_pseudo_labels_end_to_end_vs_oracle(cl4, oracle):
+    """smoothing -> peak_extract -> pseudo_label_generation on the device for a batch, against the
+    per-image oracle loop written as train.py:429-466 drives the reference."""
+    from cl4wsis_b200.modules.utils import pseudo_label_generation_batch
+    from cl4wsis_b200.wss.utils import peak_extract_device, smoothing
+    rng = np.random.default_rng(99)
+    B, C, H, W = 3, 20, 256, 320
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    gt = np.zeros((B, H, W), np.int64)
+    cam = (0.05 * rng.random((B, C, H, W))).astype(np.float32)
+    lab = np.zeros((B, C), np.float32)
+    for b in range(B):
+        for _ in range(10):
+            cls = int(rng.integers(0, C)); cy, cx = int(rng.integers(10, H - 10)), int(rng.integers(10, W - 10))
+            ry, rx = int(rng.integers(3, 40)), int(rng.integers(3, 40))
+            gt[b][((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1] = cls + 1
+            lab[b, cls] = float(rng.random() < 0.8)
+            for _p in range(int(rng.integers(0, 3))):  # 0, 1 or 2 CAM peaks per blob
+                py, px = cy + int(rng.integers(-2, 3)), cx + int(rng.integers(-2, 3))
+                cam[b, cls] = np.maximum(cam[b, cls], rng.uniform(0.6, 1.0) * np.exp(-((yy - py) ** 2 + (xx - px) ** 2) / 50).astype(np.float32))
+    sm = smoothing(cuda(cam))
+    peaks = peak_extract_device(sm, kernel=15, K=25)
+    c, o, w, m = pseudo_label_generation_batch(cuda(gt), peaks, cuda(lab), 0.7, 6)
+    sm_o = oracle.labelgen.smoothing(cam)
+    np.testing.assert_allclose(sm.cpu().numpy(), sm_o, rtol=1e-6, atol=1e-7)
+    conf, ys, xs = oracle.peak_extract(sm.cpu().numpy(), 15, 25)  # same smoothed map: isolates the label generation
+    gsn = oracle.labelgen.gaussian(6)
+    total = 0
+    for b in range(B):
+        pts = []
+        for l in np.nonzero(lab[b])[0]:
+            for cf, x, y in zip(conf[b, l], xs[b, l], ys[b, l]):
+                if cf < np.float32(0.7):
+                    break
+                pts.append([x, y, l, cf])
+        wc, wo, ww, n = oracle.labelgen.pseudo_label_generation(gt[b], pts, lab[b], C, 6, gsn)
+        assert int(m[b]) == n
+        total += n
+        assert np.array_equal(c[b].cpu().numpy(), wc) and np.array_equal(o[b].cpu().numpy(), wo)
+        assert np.array_equal(w[b].cpu().numpy(), ww)
+    assert total >= 3
