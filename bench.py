@@ -78,7 +78,7 @@ def synth_inputs(cfg, seed, n_images=None):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples SM clock and throttle reasons during the timed region (NVML, 100 ms period)."""
+    """Samples SM clock and throttle reasons during the timed region (NVML, 20 ms period)."""
 
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -114,7 +114,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def start(self):
         if self.nv is not None:
@@ -186,18 +186,74 @@ def run_reference_arm(args, cfg, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------- widened rows
+def time_callers(cfg, dev, seed):
+    """refine_label_generation and smoothing -> peak_extract -> pseudo_label_generation for one batch of
+    the workload's shape (20 fg classes), CUDA-event timed; reported next to the headline, not part of it."""
+    from cl4wsis_b200.modules import utils as mu
+    from cl4wsis_b200.wss.utils import peak_extract_device, smoothing
+    B, H, W, C = cfg["B"], cfg["H"], cfg["W"], 20
+    g = torch.Generator(device=dev).manual_seed(seed)
+    yy = torch.arange(H, device=dev, dtype=torch.float32).view(1, H, 1)
+    xx = torch.arange(W, device=dev, dtype=torch.float32).view(1, 1, W)
+    gt = torch.zeros((B, H, W), dtype=torch.int64, device=dev)
+    heat = 0.05 * torch.rand((B, C, H, W), generator=g, device=dev)
+    off = 0.3 * torch.randn((B, 2, H, W), generator=g, device=dev) + 40
+    lab = torch.zeros((B, C), device=dev)
+    for _ in range(8):  # 8 elliptic instances per image
+        cls = torch.randint(0, C, (B,), generator=g, device=dev)
+        cy = torch.randint(20, H - 20, (B, 1, 1), generator=g, device=dev).float()
+        cx = torch.randint(20, W - 20, (B, 1, 1), generator=g, device=dev).float()
+        ry = torch.randint(10, max(11, H // 6), (B, 1, 1), generator=g, device=dev).float()
+        rx = torch.randint(10, max(11, W // 6), (B, 1, 1), generator=g, device=dev).float()
+        m = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1
+        gt = torch.where(m, (cls + 1).view(B, 1, 1), gt)
+        bump = 0.9 * torch.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / 72)
+        for b in range(B):
+            lab[b, cls[b]] = 1
+            heat[b, cls[b]] = torch.maximum(heat[b, cls[b]], bump[b])
+        off[:, 0] = torch.where(m, cy - yy, off[:, 0])
+        off[:, 1] = torch.where(m, cx - xx, off[:, 1])
+    seg = torch.randn((B, C + 1, H, W), generator=g, device=dev)
+    seg.scatter_add_(1, gt[:, None], torch.full((B, 1, H, W), 3.0, device=dev))
+
+    class A:
+        refine_thresh, kernel, beta, sigma = 0.3, 41, 3.0, 6
+
+    def ev_time(fn, n=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    out, status = mu.refine_label_generation_device(seg, heat, off, lab, gt, 10000, A)
+    res = {"shape": f"B{B} C{C} {H}x{W}", "refine_status": int(status.item()),
+           "refine_weighted_px": int((out["weight"] > 0).sum())}
+    res["refine_label_generation_ms"] = ev_time(lambda: mu.refine_label_generation_device(seg, heat, off, lab, gt, 10000, A))
+    res["smooth_peak_pseudo_labels_ms"] = ev_time(
+        lambda: mu.pseudo_label_generation_batch(gt, peak_extract_device(smoothing(heat), 15, 25), lab, 0.7, 6))
+    return res
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="voc_b16_c21_512", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-images", type=int, default=16, help="images in the bounded cpu_baseline sample")
+    ap.add_argument("--cpu-images", type=int, default=64, help="images in the bounded cpu_baseline sample")
     ap.add_argument("--ref-images", type=int, default=4, help="images per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-callers", action="store_true", help="skip the timing of the widened rows (refine / pseudo labels)")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
 
@@ -277,6 +333,10 @@ def main():
                "d2h_bytes_per_step": pipe.d2h_bytes, "timing": "wall clock around K pipelined steps, sync on both sides"}
         del pipe
 
+    callers = None
+    if rank == 0 and not args.no_callers:
+        callers = time_callers(cfg, dev, 4321)
+
     # leave the process group cleanly before anything is printed (NCCL warns on stderr otherwise)
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         cdist.barrier()
@@ -290,6 +350,9 @@ def main():
     pamr_bytes_iter = 4.0 * H * W * (3 + P + T * (P + 2 * C))      # per image
     pamr_flops = 2.0 * C * P * T * H * W
     per_img_s = stats["elapsed_s"] / (B * K_)
+    tiles = B * ((H + 31) // 32) * ((W + 31) // 32)
+    smem_bytes = tiles * C * (1024 * 143.0 + 80 * 80 * 4.0) if len(dil) == 6 else float("nan")
+    sm_hz = (clk.get("sm_mhz") or 1965) * 1e6
     # dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch from the committed ncu --set full
     # capture of this workload (profiles/r01_sweep_ncu_raw.csv); other workloads were not captured
     traffic = 1.917e9 if args.workload == "voc_b16_c21_512" else None
@@ -304,10 +367,16 @@ def main():
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": sweep_bytes, "mean_launch_ms": sweep_ms},
         "path_roofline": {"bytes_iter_frac_of_hbm": pamr_bytes_iter / per_img_s / 1e9 / peak,
-                          "fp32_tflops": pamr_flops / per_img_s / 1e12, "fp32_frac_of_74.4": pamr_flops / per_img_s / 74.4e12},
+                          "fp32_tflops": pamr_flops / per_img_s / 1e12, "fp32_frac_of_74.4": pamr_flops / per_img_s / 74.4e12,
+                          # what actually binds the sweep: 143 LDS words per 4 pixel-classes
+                          # plus the 80x80 TMA window per 1024 pixel-classes, against 128 B/clk/SM
+                          "sweep_smem_bytes_per_launch": smem_bytes,
+                          "sweep_smem_frac_of_peak": smem_bytes / (sweep_ms * 1e-3) / (148 * 128 * sm_hz)},
         "e2e": e2e, "gpu_launches": K_ * step.launches_per_step, "clocks": clk,
         "checksums": {"mask": stats["checksum_mask"], "ids": stats["checksum_ids"]},
     }
+    if callers is not None:
+        line["callers"] = callers
     if world == 1 and not args.no_cpu_baseline:
         ips, dt, cores = time_oracle(cfg, args.cpu_images, 1234)
         line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
