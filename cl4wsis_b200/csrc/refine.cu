@@ -69,17 +69,34 @@ __device__ __forceinline__ float unorderable(unsigned u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// ---- 1. contours
-__global__ void ref_init_kernel(const long long* __restrict__ gt, const float* __restrict__ label, RefDims d,
-                                int* __restrict__ root) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (i >= d.HW) return;
-    const long long L = gt[(size_t)b * d.HW + i];
-    const bool valid = L >= 1 && L <= d.C && label[(size_t)b * d.C + (L - 1)] != 0.f;  // np.nonzero(label[b]) :299
-    root[(size_t)b * d.HW + i] = valid ? i : -1;
+// ---- 1. contours.  A warp labels 32 consecutive pixels of a row: every pixel starts out pointing at
+// the first pixel of its horizontal run inside the 32-pixel segment (one ballot instead of 31 unions).
+__global__ void __launch_bounds__(256)
+ref_init_kernel(const long long* __restrict__ gt, const float* __restrict__ label, RefDims d, int wpr,
+                int* __restrict__ root) {
+    const int lane = threadIdx.x & 31;
+    const int xw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (xw >= wpr) return;
+    const int x = xw * 32 + lane;
+    long long L = 0;
+    bool valid = false;
+    if (x < d.W) {
+        L = gt[(size_t)b * d.HW + y * d.W + x];
+        valid = L >= 1 && L <= d.C && label[(size_t)b * d.C + (L - 1)] != 0.f;  // np.nonzero(label[b])  :299
+    }
+    const long long Lleft = __shfl_up_sync(0xffffffffu, L, 1);
+    const bool joins = lane > 0 && valid && Lleft == L;  // same label as the pixel to the left (hence valid too)
+    const unsigned m = __ballot_sync(0xffffffffu, joins);
+    if (x < d.W) {
+        const unsigned starts = ~m & (0xffffffffu >> (31 - lane));  // run starts at or before this lane
+        root[(size_t)b * d.HW + y * d.W + x] = valid ? y * d.W + xw * 32 + (31 - __clz(starts)) : -1;
+    }
 }
 
+// Links between runs: with a = NW, b = N, c = NE, d = W of a pixel p (same label), every 8-connection is
+// implied by these few unions — p~b is made by p only when it has no d (otherwise d's own links reach
+// b's run), p~c only when there is no b, p~a only when there is neither b nor d.
 __global__ void ref_merge8_kernel(const long long* __restrict__ gt, RefDims d, int* __restrict__ root_all) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -90,11 +107,16 @@ __global__ void ref_merge8_kernel(const long long* __restrict__ gt, RefDims d, i
     const int i = y * d.W + x;
     if (root[i] < 0) return;
     const long long L = g[i];  // equal label => same (valid) class: connectivity 8 of (seg == cls+1), :305-307
-    if (x > 0 && g[i - 1] == L) ccl_union(root, i, i - 1);
+    const bool hd = x > 0 && g[i - 1] == L;
+    if (hd && (x & 31) == 0) ccl_union(root, i, i - 1);  // runs continue across 32-pixel segments
     if (y > 0) {
-        if (g[i - d.W] == L) ccl_union(root, i, i - d.W);
-        if (x > 0 && g[i - d.W - 1] == L) ccl_union(root, i, i - d.W - 1);
-        if (x + 1 < d.W && g[i - d.W + 1] == L) ccl_union(root, i, i - d.W + 1);
+        const bool hb = g[i - d.W] == L;
+        if (hb) {
+            if (!hd) ccl_union(root, i, i - d.W);
+        } else {
+            if (x + 1 < d.W && g[i - d.W + 1] == L) ccl_union(root, i, i - d.W + 1);
+            if (!hd && x > 0 && g[i - d.W - 1] == L) ccl_union(root, i, i - d.W - 1);
+        }
     }
 }
 
@@ -572,7 +594,8 @@ static int run_contours(const long long* gt, const float* label, RefDims d, int 
     REF_CUDA(cudaMemsetAsync(sc.comps, 0, (char*)sc.status + 256 - (char*)sc.comps, s), "memset");
     (void)n;
     dim3 lin(ceil_div(d.HW, 256), d.B), blk(32, 8), grd(ceil_div(d.W, 32), ceil_div(d.H, 8), d.B);
-    ref_init_kernel<<<lin, 256, 0, s>>>(gt, label, d, sc.root);
+    const int wpr = ceil_div(d.W, 32);
+    ref_init_kernel<<<dim3(ceil_div(wpr, 8), d.H, d.B), 256, 0, s>>>(gt, label, d, wpr, sc.root);
     ref_merge8_kernel<<<grd, blk, 0, s>>>(gt, d, sc.root);
     ref_flatten_stats_kernel<<<grd, blk, 0, s>>>(d, sc.root, sc.area, sc.sx, sc.sy);
     ref_make_comps_kernel<<<lin, 256, 0, s>>>(gt, d, sc.root, sc.area, sc.sx, sc.sy, min_area, sc.comp, sc.comps, sc.ncomp,
