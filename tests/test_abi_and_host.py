@@ -2,6 +2,8 @@
 declares (no compute calls), the ctypes table matches the header, and host-side argument
 validation mirrors the reference's error behaviour without touching a GPU."""
 import ctypes
+
+import numpy as np
 import os
 import re
 
@@ -97,3 +99,24 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(d, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "cl4_oracle" not in src, f
+
+
+def test_opencv_8_connectivity_label_order_rule():
+    """Host logic of the validation twin: the order in which OpenCV numbers 8-connected components
+    (2x2-block raster scan) reproduced from (first pixel, first block column) — checked against cv2."""
+    import cv2
+    from cl4wsis_b200.dataset.utils import _opencv_label_order
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        H, W = int(rng.integers(4, 40)), int(rng.integers(4, 40))
+        m = (rng.random((H, W)) < rng.uniform(0.2, 0.7)).astype(np.uint8)
+        n, lab, _, _ = cv2.connectedComponentsWithStats(m, connectivity=8)
+        # hand the function a scrambled slot numbering, as the GPU's atomically assigned slots are
+        perm = rng.permutation(n - 1)
+        comp = np.full((H, W), -1, np.int32)
+        info = np.zeros((n - 1, 5), np.int32)
+        for k in range(1, n):
+            comp[lab == k] = perm[k - 1]
+            info[perm[k - 1], 0] = np.flatnonzero((lab == k).ravel())[0]
+        order = _opencv_label_order(comp, info, list(range(n - 1)))
+        assert order == [int(perm[k - 1]) for k in range(1, n)]

@@ -541,3 +541,30 @@ def test_phase2_pseudo_labels_end_to_end_vs_oracle(cl4, oracle):
         assert np.array_equal(c[b].cpu().numpy(), wc) and np.array_equal(o[b].cpu().numpy(), wo)
         assert np.array_equal(w[b].cpu().numpy(), ww)
     assert total >= 3
+
+
+# --------------------------------------------------------------------------- validation path
+class _VArgs:
+    pass
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_get_ins_map_golden(cl4, golden_more, ci):
+    """dataset/utils.py:795-902 (Trainer.validate, train.py:622) against reference outputs: same
+    instances in the same order, masks and labels bit-exact, scores to fp32 rounding."""
+    from cl4wsis_b200.dataset.utils import get_ins_map
+    g = golden_more("insmap")
+    k = f"insmap_{ci}__"
+    a = _VArgs()
+    a.val_thresh, a.val_kernel, a.beta, ign, flip, clean = g[k + "args"].tolist()
+    a.val_kernel, a.val_ignore, a.val_flip, a.val_clean = int(a.val_kernel), bool(ign), bool(flip), bool(clean)
+    out = {n: cuda(g[k + n]) for n in ("seg", "center", "offset")}
+    tgt = tuple(int(v) for v in g[k + "target"])
+    seg_map, pl, pm, ps = get_ins_map(out, cuda(g[k + "cls_label"]), tgt, torch.device("cuda"), a)
+    assert np.array_equal(seg_map, g[k + "seg_map"])
+    assert np.array_equal(pl, g[k + "pred_label"])
+    shape = tuple(g[k + "pred_mask_shape"])
+    want_mask = np.unpackbits(g[k + "pred_mask"], axis=-1)[..., :shape[-1]].astype(bool)
+    assert pm.shape == shape and pm.dtype == np.bool_ and np.array_equal(pm, want_mask)
+    np.testing.assert_allclose(ps, g[k + "pred_score"], rtol=2e-6, atol=0)
+    assert np.array_equal(out["offset"].cpu().numpy(), g[k + "offset_after"])  # rescaled in place, as the reference
