@@ -43,13 +43,15 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
     // planes: [class][ping-pong][PITCH][PITCH]
     auto plane = [&](int c, int which) -> float* { return smem + (size_t)(c * 2 + which) * kPlane; };
 
-    // ---- stage the input masks as replicate-padded planes
+    // ---- stage the input masks as replicate-padded planes (a warp per padded row, lanes over columns:
+    // no integer division in these loops)
     for (int c = 0; c < nc; ++c) {
         const float* src = mask_in + ((size_t)b * C + c0 + c) * HW;
         float* dst = plane(c, 0);
-        for (int i = tid; i < Hp * Wp; i += kSweepThreads) {
-            const int py = i / Wp, px = i - py * Wp;
-            dst[py * PITCH + px] = __ldg(src + (size_t)clampi(py - kHalo, 0, H - 1) * W + clampi(px - kHalo, 0, W - 1));
+        for (int py = wrp; py < Hp; py += kSweepThreads / 32) {
+            const float* srow = src + (size_t)clampi(py - kHalo, 0, H - 1) * W;
+            float* drow = dst + py * PITCH;
+            for (int px = lane; px < Wp; px += 32) drow[px] = __ldg(srow + clampi(px - kHalo, 0, W - 1));
         }
     }
 
@@ -115,19 +117,20 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
         for (int c = 0; c < nc; ++c) {
             float* pl = plane(c, nxt);
             // rows above and below the image: full padded width
-            for (int i = tid; i < 2 * kHalo * Wp; i += kSweepThreads) {
-                const int r = i / Wp, px = i - r * Wp;
+            for (int r = wrp; r < 2 * kHalo; r += kSweepThreads / 32) {
                 const int py = (r < kHalo) ? r : (H + r);
-                const int sy = (r < kHalo) ? kHalo : (H + kHalo - 1);
-                pl[py * PITCH + px] = pl[sy * PITCH + clampi(px, kHalo, W + kHalo - 1)];
+                const float* srow = pl + ((r < kHalo) ? kHalo : (H + kHalo - 1)) * PITCH;
+                float* drow = pl + py * PITCH;
+                for (int px = lane; px < Wp; px += 32) drow[px] = srow[clampi(px, kHalo, W + kHalo - 1)];
             }
-            // left and right bands of the image rows
-            for (int i = tid; i < H * 2 * kHalo; i += kSweepThreads) {
-                const int r = i / (2 * kHalo), q = i - r * (2 * kHalo);
-                const int py = r + kHalo;
-                const int px = (q < kHalo) ? q : (W + q);
-                const int sx = (q < kHalo) ? kHalo : (W + kHalo - 1);
-                pl[py * PITCH + px] = pl[py * PITCH + sx];
+            // left and right bands of the image rows: lanes 0..23 left, the next 24 right
+            for (int r = wrp; r < H; r += kSweepThreads / 32) {
+                float* row = pl + (r + kHalo) * PITCH;
+                const float vl = row[kHalo], vr = row[W + kHalo - 1];
+                if (lane < kHalo) {
+                    row[lane] = vl;
+                    row[W + kHalo + lane] = vr;
+                }
             }
         }
         __syncthreads();
