@@ -354,8 +354,8 @@ def main():
     smem_bytes = tiles * C * (1024 * 143.0 + 80 * 80 * 4.0) if len(dil) == 6 else float("nan")
     sm_hz = (clk.get("sm_mhz") or 1965) * 1e6
     # dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch from the committed ncu --set full
-    # capture of this workload (profiles/r01_sweep_ncu_raw.csv); other workloads were not captured
-    traffic = 1.917e9 if args.workload == "voc_b16_c21_512" else None
+    # capture of this workload (profiles/r01b_sweep_ncu_raw.csv); other workloads were not captured
+    traffic = 1.892e9 if args.workload == "voc_b16_c21_512" else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
         "ms_per_step": 1e3 * stats["elapsed_s"] / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
