@@ -34,6 +34,7 @@ def patch_reference(wss_modules=None, wss_utils=None, modules_utils=None):
         wss_modules.PAMR = wm.PAMR
     if wss_utils is not None:
         wss_utils.peak_extract = wu.peak_extract
+        wss_utils.smoothing = wu.smoothing
     if modules_utils is not None:
         modules_utils.find_instance_center = mu.find_instance_center
         modules_utils.group_pixels = mu.group_pixels
