@@ -112,16 +112,41 @@ struct FastTile {
     template <bool kThreshold>
     __device__ static void stage_and_columns(const float* __restrict__ plane, int H, int W, int y0, int x0, float thr,
                                              int* s_key, int* s_col) {
-        for (int i = threadIdx.x; i < kRows * kCols; i += kNmsThreads) {
-            const int ty = i / kCols, tx = i - ty * kCols;
-            const int y = y0 + ty - R, x = x0 + tx - R;
-            int k = kKeyPad;
-            if (y >= 0 && y < H && x >= 0 && x < W) {
-                float v = __ldg(plane + (size_t)y * W + x);
-                if (kThreshold) v = (v <= thr) ? -1.f : v;  // F.threshold(x, thr, -1)
-                k = float_key(v);
+        // a warp per staged row, lanes over its columns: coalesced loads, no integer division; all loads
+        // of a warp are issued before the first one is consumed
+        const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;
+        constexpr int kRowsPerWarp = (kRows + kWarpsPerBlock - 1) / kWarpsPerBlock, kIts = (kCols + 31) / 32;
+        float v[kRowsPerWarp][kIts];
+#pragma unroll
+        for (int q = 0; q < kRowsPerWarp; ++q) {
+            const int y = y0 + warp_ + q * kWarpsPerBlock - R;
+            const bool row_in = (warp_ + q * kWarpsPerBlock < kRows) && y >= 0 && y < H;
+            const float* prow = plane + (size_t)(row_in ? y : 0) * W;
+#pragma unroll
+            for (int it = 0; it < kIts; ++it) {
+                const int x = x0 + it * 32 + lane_ - R;
+                v[q][it] = (row_in && it * 32 + lane_ < kCols && x >= 0 && x < W) ? __ldg(prow + x) : -INFINITY;
             }
-            s_key[ty * kPitch + tx] = k;
+        }
+#pragma unroll
+        for (int q = 0; q < kRowsPerWarp; ++q) {
+            const int ty = warp_ + q * kWarpsPerBlock;
+            const int y = y0 + ty - R;
+            const bool row_in = y >= 0 && y < H;
+#pragma unroll
+            for (int it = 0; it < kIts; ++it) {
+                const int tx = it * 32 + lane_;
+                const int x = x0 + tx - R;
+                if (ty < kRows && tx < kCols) {
+                    int k = kKeyPad;
+                    if (row_in && x >= 0 && x < W) {
+                        float t = v[q][it];
+                        if (kThreshold) t = (t <= thr) ? -1.f : t;  // F.threshold(x, thr, -1)
+                        k = float_key(t);
+                    }
+                    s_key[ty * kPitch + tx] = k;
+                }
+            }
         }
         __syncthreads();
         for (int q = threadIdx.x; q < kCols * (kTileH / kRun); q += kNmsThreads) {
@@ -466,7 +491,12 @@ peak_tile_fast_kernel(const float* __restrict__ heat, int H, int W, int K, int t
     const int y0 = (tile / tiles_x) * kTileH, x0 = (tile % tiles_x) * kTileW;
     T::template stage_and_columns<false>(heat + (size_t)plane_id * H * W, H, W, y0, x0, 0.f, s_key, s_col);
 
+    // peak = heat * keep (wss/utils.py:11-13) is exactly 0 for almost every pixel (everything that is
+    // not a local maximum), and all those zeros tie on the score: among them only the K lowest flat
+    // indices can reach the top-K.  So only NON-ZERO peaks go through the warp selection network; the
+    // zero-peak pixels are recorded as one bit each and the tile's fillers are read off the bit rows.
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ uint32_t s_zero[kTileH][kTileW / 32];
     WarpTopK<KPL> top;
     top.init(K);
 #pragma unroll
@@ -474,22 +504,32 @@ peak_tile_fast_kernel(const float* __restrict__ heat, int H, int W, int K, int t
         const int ty = pass * 16 + warp * 2 + (lane >> 4), q4 = lane & 15;
         int mx[4];
         T::row_max4(s_col, ty, q4, mx);
+        unsigned zbits = 0;
+        unsigned long long keys[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int kv = s_key[(ty + R) * T::kPitch + R + 4 * q4 + j];
             const int y = y0 + ty, x = x0 + 4 * q4 + j;
-            unsigned long long key = 0ull;
+            keys[j] = 0ull;
             if (y < H && x < W) {
-                // peak = heat * keep (wss/utils.py:11-13): the value itself where it equals the window
-                // maximum; otherwise heat*0, i.e. 0 for finite heat and NaN for NaN / +-inf heat
+                // the value itself where it equals the window maximum; otherwise heat*0, i.e. 0 for finite
+                // heat and NaN for NaN / +-inf heat
                 int pk;
                 if (kv == mx[j] && kv != kKeyNaN) pk = kv;
                 else pk = (kv == kKeyNaN || kv == 0x7f800000 || kv == (int)0x807fffff) ? kKeyNaN : 0;
-                key = ((unsigned long long)((unsigned)pk ^ 0x80000000u) << 32) |
-                      (unsigned long long)(0xffffffffu - (unsigned)(y * W + x));
+                if (pk == 0) zbits |= 1u << j;
+                else keys[j] = ((unsigned long long)((unsigned)pk ^ 0x80000000u) << 32) |
+                               (unsigned long long)(0xffffffffu - (unsigned)(y * W + x));
             }
-            top.offer(key, lane);
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (__any_sync(0xffffffffu, keys[j] != 0ull)) top.offer(keys[j], lane);
+        // 32-pixel words of the zero-peak mask: 8 lanes make a word (as in center_flags_fast_kernel)
+        unsigned word = zbits << (4 * (lane & 7));
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) word |= __shfl_xor_sync(0xffffffffu, word, o);
+        if ((lane & 7) == 0) s_zero[ty][(lane >> 3) & 1] = word;
     }
     __syncthreads();
     unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_i);
@@ -499,12 +539,47 @@ peak_tile_fast_kernel(const float* __restrict__ heat, int H, int W, int K, int t
     if (warp == 0) {
         WarpTopK<KPL> fin;
         fin.init(K);
-        for (int i = lane; i < kWarpsPerBlock * 32 * KPL; i += 32) fin.offer(s_keys[i], lane);
+        for (int i0 = 0; i0 < kWarpsPerBlock * 32 * KPL; i0 += 32) {
+            const unsigned long long c = s_keys[i0 + lane];
+            if (__any_sync(0xffffffffu, c != 0ull)) fin.offer(c, lane);
+        }
+        // order of the tile's best: positive peaks (sorted), then zero peaks by ascending index, then
+        // negative peaks (sorted); the list holds the non-zero ones
+        constexpr unsigned long long kZeroLo = 0x80000000ull << 32;  // smallest key with score +0.0
+        int n_pos = 0;
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) n_pos += __popc(__ballot_sync(0xffffffffu, fin.k[i] >= kZeroLo));
+        // zero-peak pixels per tile row (lane = row), exclusive prefix over the rows
+        const unsigned z0 = s_zero[lane][0], z1 = s_zero[lane][1];
+        const int cnt = __popc(z0) + __popc(z1);
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const int n_zero = __shfl_sync(0xffffffffu, inc, 31);
+        const int n_fill = max(0, min(K - n_pos, n_zero));
         unsigned long long* dst = cand + ((size_t)plane_id * tiles_per_plane + tile) * K;
 #pragma unroll
         for (int i = 0; i < KPL; ++i) {
             const int gi = i * 32 + lane;
-            if (gi < K) dst[gi] = fin.k[i];
+            const unsigned long long kk = fin.k[i];
+            const int slot = (kk >= kZeroLo) ? gi : gi + n_fill;  // negatives move behind the fillers
+            if (gi < K && slot < K) dst[slot] = kk;               // kk == 0 marks an unused slot
+        }
+        // fillers: this row's zero-peak pixels with tile-wide rank < n_fill
+        int rank = inc - cnt;
+        const unsigned y = (unsigned)(y0 + lane);
+        for (int half = 0; half < 2 && rank < n_fill; ++half) {
+            unsigned m = half ? z1 : z0;
+            while (m && rank < n_fill) {
+                const int bpos = __ffs(m) - 1;
+                m &= m - 1;
+                const unsigned idx = y * (unsigned)W + (unsigned)(x0 + half * 32 + bpos);
+                dst[n_pos + rank] = kZeroLo | (unsigned long long)(0xffffffffu - idx);
+                ++rank;
+            }
         }
     }
 }
