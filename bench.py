@@ -159,15 +159,23 @@ def time_oracle(cfg, n_images, seed, repeats=1, threads=None):
     return n_images / best, best, orc.num_threads()
 
 
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm overrides it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference_arm(args, cfg, rank, world):
     if rank != 0:
         return
     n_img = args.ref_images
     for _ in range(args.warmup):
-        time_oracle(cfg, 1, 999)
+        time_oracle(cfg, 1, 999, threads=host_threads())
     t_total, cores = 0.0, None
     for i in range(args.steps):
-        ips, dt, cores = time_oracle(cfg, n_img, 1234 + i)
+        ips, dt, cores = time_oracle(cfg, n_img, 1234 + i, threads=host_threads())
         t_total += dt
     value = args.steps * n_img / t_total
     sample = f"{n_img} images of workload {args.workload} per step x {args.steps} steps"
@@ -378,7 +386,7 @@ def main():
     if callers is not None:
         line["callers"] = callers
     if world == 1 and not args.no_cpu_baseline:
-        ips, dt, cores = time_oracle(cfg, args.cpu_images, 1234)
+        ips, dt, cores = time_oracle(cfg, args.cpu_images, 1234, threads=host_threads())
         line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{args.cpu_images} images of workload {args.workload}, oracle/cl4_oracle.c "
                                           f"(C+OpenMP), {dt:.1f} s"}
