@@ -168,14 +168,10 @@ static int launch_fused_one(const float* w, const float* mi, float* mo, int B, i
     static_assert(kCpbMax >= 1, "plane too large for shared memory");
     const int cpb = pick_cpb(B, C, kCpbMax);
     const size_t smem = (size_t)cpb * 2 * kPlaneBytes;
-    static size_t attr_smem = 0;  // per instantiation
-    if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            set_error("pamr_fused: smem attribute: %s", cudaGetErrorString(e));
-            return CL4_ECUDA;
-        }
-        attr_smem = smem;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // per device
+    if (e != cudaSuccess) {
+        set_error("pamr_fused: smem attribute: %s", cudaGetErrorString(e));
+        return CL4_ECUDA;
     }
     dim3 grid(ceil_div(C, cpb), B);
     kern<<<grid, kSweepThreads, smem, s>>>(w, mi, mo, C, H, W, cpb, num_iter, dil);

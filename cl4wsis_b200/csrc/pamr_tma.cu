@@ -417,14 +417,11 @@ static int launch_weights_one(const CUtensorMap& tmap, float* w, int K, int tile
                               const Dilations& dil, cudaStream_t s) {
     auto kern = pamr_weights_tma_kernel<D, DS>;
     const size_t smem = (size_t)kWeightsMaxK * kStageBytes + 64;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            set_error("pamr_weights_tma: smem attribute: %s", cudaGetErrorString(e));
-            return CL4_ECUDA;
-        }
-        attr_done = true;
+    // set on every call: the attribute is per device, and a cached flag would be wrong for a second device
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("pamr_weights_tma: smem attribute: %s", cudaGetErrorString(e));
+        return CL4_ECUDA;
     }
     kern<<<n_tiles, 256, smem, s>>>(tmap, w, K, tiles_x, tiles_per_img, dil);
     return check_launch("pamr_weights_tma");
@@ -472,14 +469,10 @@ template <int D, class DS>
 static int launch_one(const CUtensorMap& tmap, const float* w, const SweepOut& out, int C, int H, int W, int tiles_x,
                       int tiles_y, int n_tiles, const Dilations& dil, cudaStream_t s) {
     auto kern = pamr_sweep_tma_kernel<D, DS>;
-    static bool attr_done = false;  // per instantiation
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem);
-        if (e != cudaSuccess) {
-            set_error("pamr_sweep_tma: smem attribute: %s", cudaGetErrorString(e));
-            return CL4_ECUDA;
-        }
-        attr_done = true;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem);  // per device
+    if (e != cudaSuccess) {
+        set_error("pamr_sweep_tma: smem attribute: %s", cudaGetErrorString(e));
+        return CL4_ECUDA;
     }
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
     kern<<<grid, kSweepThreads, kSweepSmem, s>>>(tmap, w, out, C, H, W, tiles_x, tiles_y, n_tiles, dil);
