@@ -14,6 +14,10 @@
 #include "common.cuh"
 #include "pamr_internal.cuh"
 
+#ifndef CL4_LATTICE_DEFAULT
+#define CL4_LATTICE_DEFAULT 0
+#endif
+
 namespace cl4 {
 
 // ---------------------------------------------------------------------------------------------
@@ -211,6 +215,12 @@ static int make_dilations(const int* dilations, int D, Dilations* out) {
     return CL4_OK;
 }
 
+// weights region of the scratch: large enough for either tiled layout
+static size_t weight_scratch_elems(int B, int H, int W, int D) {
+    const size_t a = tiled_weight_elems(B, H, W, D), b = (D == 6) ? lattice_weight_elems(B, H, W) : 0;
+    return a > b ? a : b;
+}
+
 static int check_plane(const char* what, long long B, int H, int W) {
     CL4_REQUIRE(B >= 0 && H > 0 && W > 0, CL4_EINVAL, "%s: bad shape", what);
     CL4_REQUIRE((long long)H * W < (1ll << 30), CL4_EUNSUPPORTED, "%s: plane too large", what);
@@ -265,7 +275,7 @@ extern "C" int cl4_pamr_sweep(const float* w, const float* mask_in, float* mask_
 
 extern "C" size_t cl4_pamr_scratch_bytes(int B, int K, int C, int H, int W, int D, int num_iter) {
     if (B <= 0 || K <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return 0;
-    const size_t wbytes = cl4::align_up(sizeof(float) * cl4::tiled_weight_elems(B, H, W, D), 256);
+    const size_t wbytes = cl4::align_up(sizeof(float) * cl4::weight_scratch_elems(B, H, W, D), 256);
     // padded path: one replicate-padded copy of the input (+ a second ping-pong buffer from 2 sweeps on);
     // generic path: one plain ping-pong buffer.  The padded layout is the larger of the two.
     const size_t padded = cl4::align_up(sizeof(float) * (size_t)B * C * cl4::padded_plane_elems(H, W), 256);
@@ -305,14 +315,16 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
                 "pamr_forward: scratch too small");
     char* base = reinterpret_cast<char*>(scratch);
     float* wts = reinterpret_cast<float*>(base);
-    const size_t wbytes = align_up(sizeof(float) * tiled_weight_elems(B, H, W, D), 256);
+    const size_t wbytes = align_up(sizeof(float) * weight_scratch_elems(B, H, W, D), 256);
     const size_t padded = align_up(sizeof(float) * (size_t)B * C * padded_plane_elems(H, W), 256);
     float* bufA = reinterpret_cast<float*>(base + wbytes);
     float* bufB = reinterpret_cast<float*>(base + wbytes + padded);
     // CL4_SWEEP=v1 forces the register/L1 kernel, CL4_SWEEP=tma skips the fused small-map kernel
     // (A/B timing and tests of the other paths)
+    // CL4_SWEEP=lattice / nolattice: take / skip the lattice sweep wherever it applies
     const char* force = getenv("CL4_SWEEP");
     const bool force_v1 = force && strcmp(force, "v1") == 0, force_tma = force && strcmp(force, "tma") == 0;
+    const bool force_lat = force && strcmp(force, "lattice") == 0, no_lat = force && strcmp(force, "nolattice") == 0;
     if (!force_v1 && !force_tma && pamr_fused_applicable(H, W, dil, D)) {
         // small maps (the trainer's feature resolution): weights, then every iteration in one launch
         rc = dispatch_D<WeightsLauncher>(D, img, wts, B, K, H, W, dil, 1, s);
@@ -323,7 +335,13 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
         return record(ev_sweeps_end);
     }
     const bool use_tma = !force_v1 && sweep_tma_applicable(H, W, dil, D);
-    if (use_tma && weights_tma_applicable(K)) {
+    const bool use_lattice = use_tma && !force_tma && !no_lat && sweep_lattice_applicable(K, H, W, dil, D) &&
+                             (force_lat || CL4_LATTICE_DEFAULT);
+    if (use_lattice) {
+        float* pimg = reinterpret_cast<float*>(base + wbytes + (num_iter >= 2 ? 2 : 1) * padded);
+        rc = launch_pad_copy(img, pimg, (long long)B * K, H, W, s);
+        if (rc == CL4_OK) rc = launch_weights_lattice(pimg, wts, B, K, H, W, s);
+    } else if (use_tma && weights_tma_applicable(K)) {
         // image -> replicate-padded copy (scratch, after the mask buffers) -> TMA-staged weights kernel
         float* pimg = reinterpret_cast<float*>(base + wbytes + (num_iter >= 2 ? 2 : 1) * padded);
         rc = launch_pad_copy(img, pimg, (long long)B * K, H, W, s);
@@ -342,7 +360,8 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
         float* nxt = bufB;
         for (int it = 0; it < num_iter; ++it) {
             const bool last = (it == num_iter - 1);
-            rc = launch_sweep_tma(wts, cur, last ? mask_out : nxt, last ? 0 : 1, B, C, H, W, dil, D, s);
+            rc = use_lattice ? launch_sweep_lattice(wts, cur, last ? mask_out : nxt, last ? 0 : 1, B, C, H, W, s)
+                             : launch_sweep_tma(wts, cur, last ? mask_out : nxt, last ? 0 : 1, B, C, H, W, dil, D, s);
             if (rc != CL4_OK) return rc;
             if (!last) {
                 rc = launch_pad_frame(nxt, planes, H, W, s);

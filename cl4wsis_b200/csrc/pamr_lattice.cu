@@ -1,0 +1,534 @@
+// PAMR propagation sweep, "lattice" variant for the dilation set [1,2,4,8,12,24]
+// (PAMR's class default, reference wss/modules.py:125; the sweep itself is :148-149).
+//
+// Why.  The TMA sweep in pamr_tma.cu is bound by shared-memory bandwidth: every FMA needs one
+// weight (reused across the C classes -> registers) and one source value (reused only across
+// different (pixel, tap) pairs -> shared memory), and with four pixels x 48 taps per thread only
+// 49 of 192 sources coincide (143 LDS per 192 FMA).  What a thread can reuse is decided by WHICH
+// 192 (pixel, tap) pairs its 192 weight registers belong to.  Here the CTA is split into two warp
+// groups of four warps, each thread owning 8 pixels x 24 taps:
+//   group A  dilations {4,8,12}: a 2 x 4 block of pixels on the lattice of spacing 4 (rows y0, y0+4;
+//            columns x0, x0+4, x0+8, x0+12).  Its 192 (pixel, tap) pairs touch only 76 distinct
+//            sources (steps 1, 2, 3 of the same lattice).
+//   group B  dilations {1,2,24}: a 4 x 2 block of adjacent pixels, sources read as float2:
+//            24 LDS.64 for {1,2} (an 8 x 6 patch) + 32 LDS.64 for dilation 24 = 112 wavefronts.
+// The partial sums of A meet B's in shared memory (8 STS per A thread, 4 LDS.64 per B thread, double
+// buffered per warp pair behind mbarriers); B adds and stores float2.  Per (tile, class):
+// 4*(76+8) + 4*(112+8) = 816 LDS/STS wavefronts (the 4-pixel kernel: 1144) + 210 of TMA writes.
+// Eight accumulators per thread also double the FMA-level parallelism.
+//
+// Status: opt-in (CL4_SWEEP=lattice), parity-tested, NOT the default.  It moves 27 % fewer shared-memory
+// wavefronts than the 4-pixel kernel (ncu: 72.1 M vs 98.5 M per launch) but is not faster (0.62-0.66 ms vs
+// 0.61 ms per sweep): without any TMA traffic its loop still takes 1430 cycles per (tile, class) against an
+// 816-wavefront floor, i.e. with 8 warps per SM (255 registers) the loop is bound by instruction latency and
+// by the hand-over between the groups, not by shared-memory bandwidth.  See profiles/r01c_notes.md.
+//
+//   tile    32 x 32 pixels, 256 threads; window 80 rows x 84 columns per (tile, class), one
+//           cp.async.bulk.tensor box into a ring of stages with full/empty mbarriers.  The pitch of
+//           84 floats (= 20 mod 32) makes group A's lane pattern (4 x 4 phases x 2 super-blocks)
+//           bank-conflict free; group B's half-warps read 16 adjacent float2.
+//   weights thread-major [tile][k = slot*24 + tap][thread] (written by pamr_weights_lattice_kernel),
+//           a warp's load of one k is one 128-byte run; same size as the 32x32 tile-major layout.
+#include "common.cuh"
+#include "pamr_internal.cuh"
+#include "pamr_sweep.cuh"
+#include "tma.cuh"
+
+namespace cl4 {
+
+#ifndef CL4_LATTICE_STAGES
+#define CL4_LATTICE_STAGES 6
+#endif
+#ifndef CL4_LATTICE_AHEAD
+#define CL4_LATTICE_AHEAD 2
+#endif
+
+constexpr int kLThreads = 256;                       // 8 warps: 0-3 group A, 4-7 group B
+constexpr int kLGroupThreads = 128;
+constexpr int kLPitch = 84;                          // window pitch in floats; 84 % 32 == 20
+constexpr int kLStageFloats = kBox * kLPitch;        // 80 rows x 84 columns = 6720
+constexpr int kLStageBytes = kLStageFloats * 4;      // 26880 = 210 * 128
+constexpr int kLStages = CL4_LATTICE_STAGES;
+constexpr int kLAhead = CL4_LATTICE_AHEAD;           // items in flight beyond the current one
+constexpr int kLPartPitch = 36;                      // partial sums of group A: 32 rows x 36 floats (36 % 32 == 4)
+constexpr int kLPartFloats = kTile * kLPartPitch;    // 1152
+constexpr int kLPx = 8;                              // pixels per thread
+constexpr int kLTaps = 24;                           // taps per thread and pixel (three dilations)
+constexpr int kLW = kLPx * kLTaps;                   // 192 weight registers
+constexpr int kLWeightsPerTile = kLW * kLThreads;    // 49152 floats = 48 taps x 1024 pixels
+#ifndef CL4_LATTICE_PARTS
+#define CL4_LATTICE_PARTS 4
+#endif
+#ifndef CL4_LATTICE_PRODUCER
+#define CL4_LATTICE_PRODUCER 0
+#endif
+constexpr int kLProducerGroup = CL4_LATTICE_PRODUCER;  // which group's first thread issues the TMA loads
+constexpr int kLParts = CL4_LATTICE_PARTS;           // partial-sum buffers: how far group A may run ahead of group B
+constexpr size_t kLSmem = (size_t)kLStages * kLStageBytes + kLParts * kLPartFloats * 4 + (2 * kLStages + 8 * kLParts) * 8 + 64;
+static_assert(kLAhead >= 1 && kLAhead < kLStages, "prefetch distance");
+
+// ---- who owns pixel (y, x) of a tile in each group: thread (0..127 within the group) and slot (0..7) ----
+struct Owner {
+    int thread, slot;
+};
+// group A: 2 x 4 lattice blocks of spacing 4 inside 8 x 16 super-blocks (16 threads = 4 x 4 phases)
+__host__ __device__ inline Owner owner_a(int y, int x) {
+    const int sby = y >> 3, ry = y & 7, sbx = x >> 4, rx = x & 15;
+    return Owner{(sby * 2 + sbx) * 16 + (ry & 3) * 4 + (rx & 3), (ry >> 2) * 4 + (rx >> 2)};
+}
+// group B: 4 x 2 blocks of adjacent pixels, 16 blocks per row of blocks (one half-warp)
+__host__ __device__ inline Owner owner_b(int y, int x) { return Owner{(y >> 2) * 16 + (x >> 1), (y & 3) * 2 + (x & 1)}; }
+
+// reference tap order (wss/modules.py:30-40): row-major over the 3x3 neighbourhood, centre skipped
+__host__ __device__ constexpr int tap_index(int dy, int dx) {
+    const int idx = (dy + 1) * 3 + (dx + 1);
+    return idx > 4 ? idx - 1 : idx;
+}
+// lattice offset (di, dj) in units of the spacing: is it a tap of step s (dilation s * spacing)?
+__host__ __device__ constexpr bool is_tap(int di, int dj, int s) {
+    return (di == -s || di == 0 || di == s) && (dj == -s || dj == 0 || dj == s) && !(di == 0 && dj == 0);
+}
+
+// One source value `v` at lattice position (r, c) of an A x B block whose taps are the steps 1..NS of the
+// lattice: feed every (pixel, tap) that reads it.  Weight register of (pixel slot, step s, tap): slot*24 + (s-1)*8 + tap.
+template <int A, int B, int NS, bool kReload>
+__device__ __forceinline__ void feed(float (&w)[kLW], float (&acc)[kLPx], const float v, const int r, const int c,
+                                     const float* __restrict__ nw) {
+#pragma unroll
+    for (int i = 0; i < A; ++i)
+#pragma unroll
+        for (int j = 0; j < B; ++j)
+#pragma unroll
+            for (int s = 1; s <= NS; ++s) {
+                const int di = r - i, dj = c - j;
+                if (is_tap(di, dj, s)) {
+                    const int k = (i * B + j) * kLTaps + (s - 1) * 8 + tap_index(di / s, dj / s);
+                    acc[i * B + j] = fmaf(w[k], v, acc[i * B + j]);
+                    if (kReload) w[k] = __ldg(nw + k * kLThreads);
+                }
+            }
+}
+
+template <int A, int B, int NS>
+__host__ __device__ constexpr bool source_needed(int r, int c) {
+    for (int i = 0; i < A; ++i)
+        for (int j = 0; j < B; ++j)
+            for (int s = 1; s <= NS; ++s)
+                if (is_tap(r - i, c - j, s)) return true;
+    return false;
+}
+
+// group A: 2 x 4 lattice block of spacing 4, dilations 4, 8, 12 = steps 1, 2, 3; sp points at the block's
+// pixel (0, 0) inside the window.  76 of the 8 x 10 lattice positions are read.
+template <bool kReload>
+__device__ __forceinline__ void group_a_class(float (&w)[kLW], float (&acc)[kLPx], const float* __restrict__ sp,
+                                              const float* __restrict__ nw) {
+#pragma unroll
+    for (int r = -3; r < 2 + 3; ++r)
+#pragma unroll
+        for (int c = -3; c < 4 + 3; ++c)
+            if (source_needed<2, 4, 3>(r, c)) {
+                const float v = sp[r * 4 * kLPitch + c * 4];
+                feed<2, 4, 3, kReload>(w, acc, v, r, c, nw);
+            }
+}
+
+// group B: 4 x 2 block of adjacent pixels.  Dilations 1 and 2 (steps 1, 2 of the unit lattice): rows -2..5,
+// columns -2..3 as float2.  Dilation 24 (third tap set, weights slot*24 + 16 + tap): the two pixels of a row
+// share one float2 per tap.
+template <bool kReload>
+__device__ __forceinline__ void group_b_class(float (&w)[kLW], float (&acc)[kLPx], const float* __restrict__ sp,
+                                              const float* __restrict__ nw) {
+#pragma unroll
+    for (int r = -2; r < 4 + 2; ++r)
+#pragma unroll
+        for (int c = -2; c < 4; c += 2) {
+            const float2 v = *reinterpret_cast<const float2*>(sp + r * kLPitch + c);
+            feed<4, 2, 2, kReload>(w, acc, v.x, r, c, nw);
+            feed<4, 2, 2, kReload>(w, acc, v.y, r, c + 1, nw);
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int a = -1; a <= 1; ++a)
+#pragma unroll
+            for (int b = -1; b <= 1; ++b) {
+                if (a == 0 && b == 0) continue;
+                const float2 v = *reinterpret_cast<const float2*>(sp + (i + 24 * a) * kLPitch + 24 * b);
+                const int k0 = (i * 2) * kLTaps + 16 + tap_index(a, b), k1 = k0 + kLTaps;
+                acc[i * 2] = fmaf(w[k0], v.x, acc[i * 2]);
+                acc[i * 2 + 1] = fmaf(w[k1], v.y, acc[i * 2 + 1]);
+                if (kReload) {
+                    w[k0] = __ldg(nw + k0 * kLThreads);
+                    w[k1] = __ldg(nw + k1 * kLThreads);
+                }
+            }
+}
+
+struct LatticeOut {
+    float* ptr;       // element (plane 0, y = 0, x = 0) of the output
+    long long plane;  // elements between planes
+    int pitch;        // elements between rows (even)
+};
+
+struct LatticeCtx {
+    float* stage0;
+    float* part;  // [kLParts buffers][kLPartFloats]; pfull / pempty: [kLParts][4 warp pairs]
+    uint64_t *full, *empty, *pfull, *pempty;
+    const float* wts;
+    int C, H, W, tiles_x, tiles_per_img, n_my, total, s0;
+};
+
+struct LTile {
+    int b, y0, x0;
+};
+__device__ __forceinline__ LTile ltile(int t, int tiles_x, int tiles_per_img) {
+    LTile tc;
+    tc.b = t / tiles_per_img;
+    const int r = t - tc.b * tiles_per_img;
+    const int tyi = r / tiles_x;
+    tc.y0 = tyi * kTile;
+    tc.x0 = (r - tyi * tiles_x) * kTile;
+    return tc;
+}
+
+// The item loop of one warp group (G = 0: A, G = 1: B).  Item i of this CTA is (tile ordinal, class) =
+// ((i + s0) / C mod n_my, (i + s0) mod C) as in pamr_tma.cu (staggered class phase).
+template <int G>
+__device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const CUtensorMap* tmap, const LatticeOut& out) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tg = tid - G * kLGroupThreads;
+    const int C = cx.C;
+
+    // thread geometry: tile-relative row / column of the thread's block origin
+    int ry, rx;
+    if (G == 0) {
+        const int sb = tg >> 4;
+        ry = (sb >> 1) * 8 + ((tg >> 2) & 3);
+        rx = (sb & 1) * 16 + (tg & 3);
+    } else {
+        ry = (tg >> 4) * 4;
+        rx = (tg & 15) * 2;
+    }
+    const int tb = (ry + kHalo) * kLPitch + rx + kHalo;  // window offset of the block origin
+    const int pbase = ry * kLPartPitch + rx;             // partial-buffer offset
+
+    // ---- producer: the first thread of group kLProducerGroup issues the TMA loads.  It never waits for a stage
+    // it does not need yet (non-blocking test of the empty barrier, up to kLAhead items beyond the current one)
+    // and only blocks for the current item's own window.  Measured at B16 C21 512^2 (ms per sweep incl. frame):
+    //   producer in A, 6 stages, 5 ahead: 0.80-0.83 -- group A runs up to kLParts items ahead of B, the ring depth
+    //     seen by A collapses, and random CTAs stay 1.75x slower for a whole launch (bistable; not seen under ncu);
+    //   producer in A, 2 ahead: 0.66, no slow CTAs (the default);  producer in B, 5 ahead: 0.73, A waits on `full`;
+    //   blocking producer in A with a slack of 1 / 2 / 3 items behind the slowest warp: 1.09 / 0.71-0.77 / 0.62.
+    int p_item = 0;
+    auto issue_upto = [&](int item) {
+        while (p_item < cx.total && p_item <= item + kLAhead) {
+            const int s = p_item % kLStages;
+            if (p_item >= kLStages) {
+                const uint32_t parity = (uint32_t)((p_item / kLStages - 1) & 1);
+                if (p_item == item) mbar_wait(&cx.empty[s], parity);
+                else if (!mbar_test(&cx.empty[s], parity)) break;
+            }
+            const int v = p_item + cx.s0;
+            int pk = v / C;
+            const int pc = v - pk * C;
+            if (pk == cx.n_my) pk = 0;
+            const LTile ptc = ltile(blockIdx.x + pk * gridDim.x, cx.tiles_x, cx.tiles_per_img);
+            mbar_arrive_expect_tx(&cx.full[s], kLStageBytes);
+            tma_load_3d(cx.stage0 + (size_t)s * kLStageFloats, tmap, &cx.full[s], ptc.x0, ptc.y0, ptc.b * C + pc);
+            ++p_item;
+        }
+    };
+#ifndef CL4_LATTICE_NOTMA
+    if (G == kLProducerGroup && tg == 0) issue_upto(0);
+#endif
+
+    float w[kLW];
+    float acc[kLPx];
+    auto weight_ptr = [&](int t) -> const float* { return cx.wts + (size_t)t * kLWeightsPerTile + tid; };
+    auto prefetch_next_weights = [&](int kk) {
+        int nn = kk + 1;
+        if (nn == cx.n_my) nn = 0;
+        if (nn == kk) return;
+        const float* base = cx.wts + (size_t)(blockIdx.x + nn * gridDim.x) * kLWeightsPerTile;
+        constexpr int kChunk = kLWeightsPerTile * 4 / 8;  // 24576 bytes, one per warp
+        if (lane == 0) bulk_prefetch_l2(reinterpret_cast<const char*>(base) + (size_t)(tid >> 5) * kChunk, kChunk);
+    };
+
+    int k = 0, c = cx.s0;
+    // group B finishes the pixels: store pointer and the number of valid rows of its 4 x 2 block
+    float* o = nullptr;
+    int nrows = 0;
+    auto enter_tile = [&](int kk) {
+        if (G != 1) return;
+        const LTile tc = ltile(blockIdx.x + kk * gridDim.x, cx.tiles_x, cx.tiles_per_img);
+        const int y = tc.y0 + ry, x = tc.x0 + rx;
+        nrows = (x < cx.W) ? min(max(cx.H - y, 0), 4) : 0;
+        o = out.ptr + (long long)tc.b * C * out.plane + (long long)y * out.pitch + x;
+    };
+    if (cx.total > 0) {
+        enter_tile(0);
+        prefetch_next_weights(0);
+        const float* wp = weight_ptr(blockIdx.x);
+#pragma unroll
+        for (int i = 0; i < kLW; ++i) w[i] = __ldg(wp + i * kLThreads);
+    }
+
+    for (int item = 0; item < cx.total; ++item) {
+#ifndef CL4_LATTICE_NOTMA  // ablation: compute on whatever the stages hold
+        if (G == kLProducerGroup && tg == 0) issue_upto(item);
+#endif
+
+        const int s = item % kLStages;
+        const float* sp = cx.stage0 + (size_t)s * kLStageFloats + tb;
+        int nk = k + 1;
+        if (nk == cx.n_my) nk = 0;
+        const bool reload = (c == C - 1) && (item + 1 < cx.total) && (nk != k);
+        const float* nw = weight_ptr(blockIdx.x + nk * gridDim.x);
+#ifndef CL4_LATTICE_NOTMA
+        mbar_wait(&cx.full[s], (uint32_t)((item / kLStages) & 1));
+#endif
+
+#pragma unroll
+        for (int i = 0; i < kLPx; ++i) acc[i] = 0.f;
+        if (G == 0) {
+            if (reload) group_a_class<true>(w, acc, sp, nw);
+            else group_a_class<false>(w, acc, sp, nw);
+        } else {
+            if (reload) group_b_class<true>(w, acc, sp, nw);
+            else group_b_class<false>(w, acc, sp, nw);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cx.empty[s]);  // this warp no longer reads the window
+
+        // A's warp j and B's warp j own the same 8 rows of the tile, so the hand-over is per warp pair
+        const int pb = item % kLParts, pj = pb * 4 + ((tid >> 5) & 3);
+        float* pp = cx.part + pb * kLPartFloats + pbase;
+        if (G == 0) {
+            if (item >= kLParts) mbar_wait(&cx.pempty[pj], (uint32_t)((item / kLParts - 1) & 1));
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pp[i * 4 * kLPartPitch + j * 4] = acc[i * 4 + j];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cx.pfull[pj]);
+        } else {
+            mbar_wait(&cx.pfull[pj], (uint32_t)((item / kLParts) & 1));
+            float* oc = o + (long long)c * out.plane;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 a = *reinterpret_cast<const float2*>(pp + i * kLPartPitch);
+                float2 r;
+                r.x = acc[2 * i] + a.x;
+                r.y = acc[2 * i + 1] + a.y;
+                if (i < nrows) *reinterpret_cast<float2*>(oc + (long long)i * out.pitch) = r;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cx.pempty[pj]);
+        }
+
+        if (++c == C) {
+            c = 0;
+            if (nk != k) {
+                k = nk;
+                enter_tile(k);
+                prefetch_next_weights(k);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kLThreads, 1)
+pamr_sweep_lattice_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wts, LatticeOut out, int C,
+                          int H, int W, int tiles_x, int tiles_y, int n_tiles) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    LatticeCtx cx;
+    cx.stage0 = reinterpret_cast<float*>(smem_raw);
+    cx.part = cx.stage0 + (size_t)kLStages * kLStageFloats;
+    cx.full = reinterpret_cast<uint64_t*>(cx.part + kLParts * kLPartFloats);
+    cx.empty = cx.full + kLStages;
+    cx.pfull = cx.empty + kLStages;
+    cx.pempty = cx.pfull + 4 * kLParts;
+    cx.wts = wts;
+    cx.C = C;
+    cx.H = H;
+    cx.W = W;
+    cx.tiles_x = tiles_x;
+    cx.tiles_per_img = tiles_x * tiles_y;
+    cx.n_my = (n_tiles > (int)blockIdx.x) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    cx.total = cx.n_my * C;
+    cx.s0 = (int)(((long long)blockIdx.x * C) / gridDim.x);
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int s = 0; s < kLStages; ++s) {
+            mbar_init(&cx.full[s], 1);
+            mbar_init(&cx.empty[s], kLThreads / 32);
+        }
+        for (int s = 0; s < 4 * kLParts; ++s) {
+            mbar_init(&cx.pfull[s], 1);   // warp j of group A
+            mbar_init(&cx.pempty[s], 1);  // warp j of group B
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (threadIdx.x < kLGroupThreads) lattice_group<0>(cx, &tmap, out);  // warp-uniform
+    else lattice_group<1>(cx, &tmap, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Affinity weights (reference wss/modules.py:141-145) in the lattice layout, from a replicate-padded
+// image: one CTA per 32 x 32 tile, the K (<= 3) 80 x 84 channel windows arrive by TMA, each thread
+// walks four pixels (lanes along x: conflict-free LDS at immediate offsets).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLThreads, 2)
+pamr_weights_lattice_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ wts, int K, int tiles_x,
+                            int tiles_per_img) {
+    constexpr int D = 6, P = 48;
+    using DS = DilVoc6;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float* win = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)3 * kLStageBytes);
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const LTile tc = ltile(blockIdx.x, tiles_x, tiles_per_img);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(bar, (uint32_t)(K * kLStageBytes));
+        for (int k = 0; k < K; ++k) tma_load_3d(win + (size_t)k * kLStageFloats, &tmap, bar, tc.x0, tc.y0, tc.b * K + k);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    float* o = wts + (size_t)blockIdx.x * kLWeightsPerTile;
+    const float invK = 1.f / (float)K;
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        const int y = wrp + 8 * i, x = lane;
+        const float* sp0 = win + (y + kHalo) * kLPitch + x + kHalo;
+        float logit[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) logit[p] = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+            const float* sp = sp0 + k * kLStageFloats;
+            const float c = sp[0];
+            float dlt[P];  // neighbour - centre; the D centre samples of LocalStDev contribute zeros
+#pragma unroll
+            for (int di = 0; di < D; ++di) {
+                const int d = DS::get(di);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int dy = (j < 3) ? -1 : ((j < 5) ? 0 : 1);
+                    const int dx = (j < 3) ? (j - 1) : ((j == 3) ? -1 : ((j == 4) ? 1 : (j - 6)));
+                    dlt[di * 8 + j] = sp[dy * d * kLPitch + dx * d] - c;
+                }
+            }
+            float s1 = 0.f;
+#pragma unroll
+            for (int p = 0; p < P; ++p) s1 += dlt[p];
+            const float mean = s1 * (1.f / (float)(9 * D));
+            float ss = (float)D * mean * mean;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const float t = dlt[p] - mean;
+                ss = fmaf(t, t, ss);
+            }
+            const float sd = sqrtf(ss * (1.f / (float)(9 * D - 1)));
+            const float ninv = -1.f / (1e-8f + 0.1f * sd);
+#pragma unroll
+            for (int p = 0; p < P; ++p) logit[p] = fmaf(fabsf(dlt[p]), ninv, logit[p]);
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            logit[p] *= invK;
+            mx = fmaxf(mx, logit[p]);
+        }
+        float z = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            logit[p] = __expf(logit[p] - mx);
+            z += logit[p];
+        }
+        const float rz = 1.f / z;
+        // group A holds dilations 4, 8, 12 (taps 16..39), group B dilations 1, 2 (taps 0..15) and 24 (taps 40..47)
+        const Owner oa = owner_a(y, x), ob = owner_b(y, x);
+        float* pa = o + (size_t)(oa.slot * kLTaps) * kLThreads + oa.thread;
+        float* pb = o + (size_t)(ob.slot * kLTaps) * kLThreads + kLGroupThreads + ob.thread;
+#pragma unroll
+        for (int t = 0; t < 24; ++t) pa[t * kLThreads] = logit[16 + t] * rz;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) pb[t * kLThreads] = logit[t] * rz;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) pb[(16 + t) * kLThreads] = logit[40 + t] * rz;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+bool sweep_lattice_applicable(int K, int H, int W, const Dilations& dil, int D) {
+    if (D != 6 || K < 1 || K > 3) return false;
+    for (int i = 0; i < 6; ++i)
+        if (dil.d[i] != DilVoc6::get(i)) return false;
+    if (W % 4 != 0) return false;                   // TMA: 16-byte global row pitch; float2 stores
+    if ((long long)H * W <= 64 * 64) return false;  // small maps: the fused kernel
+    return true;
+}
+
+size_t lattice_weight_elems(int B, int H, int W) {
+    return (size_t)B * ceil_div(H, kTile) * ceil_div(W, kTile) * (size_t)kLWeightsPerTile;
+}
+
+int launch_weights_lattice(const float* padded_img, float* w, int B, int K, int H, int W, cudaStream_t s) {
+    CUtensorMap tmap;
+    const int rc = encode_tmap_3d_f32(&tmap, padded_img, W + 2 * kHalo, H + 2 * kHalo, (long long)B * K, kLPitch, kBox);
+    if (rc != 0) {
+        set_error("pamr_weights_lattice: cuTensorMapEncodeTiled failed (%d)", rc);
+        return CL4_ECUDA;
+    }
+    const int tiles_x = ceil_div(W, kTile), tiles_y = ceil_div(H, kTile);
+    const int n_tiles = B * tiles_x * tiles_y;
+    const size_t smem = (size_t)3 * kLStageBytes + 64;
+    cudaError_t e = cudaFuncSetAttribute(pamr_weights_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("pamr_weights_lattice: smem attribute: %s", cudaGetErrorString(e));
+        return CL4_ECUDA;
+    }
+    pamr_weights_lattice_kernel<<<n_tiles, kLThreads, smem, s>>>(tmap, w, K, tiles_x, tiles_x * tiles_y);
+    return check_launch("pamr_weights_lattice");
+}
+
+int launch_sweep_lattice(const float* w, const float* padded_in, float* out, int out_padded, int B, int C, int H, int W,
+                         cudaStream_t s) {
+    CUtensorMap tmap;
+    const int Wp = W + 2 * kHalo, Hp = H + 2 * kHalo;
+    const int rc = encode_tmap_3d_f32(&tmap, padded_in, Wp, Hp, (long long)B * C, kLPitch, kBox);
+    if (rc != 0) {
+        set_error("pamr_sweep_lattice: cuTensorMapEncodeTiled failed (%d)", rc);
+        return CL4_ECUDA;
+    }
+    LatticeOut so;
+    if (out_padded) {
+        so.ptr = out + (size_t)kHalo * Wp + kHalo;
+        so.plane = (long long)Hp * Wp;
+        so.pitch = Wp;
+    } else {
+        so.ptr = out;
+        so.plane = (long long)H * W;
+        so.pitch = W;
+    }
+    const int tiles_x = ceil_div(W, kTile), tiles_y = ceil_div(H, kTile);
+    const int n_tiles = B * tiles_x * tiles_y;
+    cudaError_t e = cudaFuncSetAttribute(pamr_sweep_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmem);
+    if (e != cudaSuccess) {
+        set_error("pamr_sweep_lattice: smem attribute: %s", cudaGetErrorString(e));
+        return CL4_ECUDA;
+    }
+    const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+    pamr_sweep_lattice_kernel<<<grid, kLThreads, kLSmem, s>>>(tmap, w, so, C, H, W, tiles_x, tiles_y, n_tiles);
+    return check_launch("pamr_sweep_lattice");
+}
+
+}  // namespace cl4
+

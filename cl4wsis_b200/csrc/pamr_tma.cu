@@ -32,7 +32,12 @@ namespace cl4 {
 #ifndef CL4_SWEEP_PRODUCER
 #define CL4_SWEEP_PRODUCER 0
 #endif
+#ifndef CL4_SWEEP_AHEAD
+#define CL4_SWEEP_AHEAD (CL4_SWEEP_STAGES - 1)
+#endif
 constexpr int kStages = CL4_SWEEP_STAGES;
+constexpr int kAhead = CL4_SWEEP_AHEAD;  // windows in flight beyond the current item (< kStages)
+static_assert(kAhead >= 1 && kAhead < kStages, "prefetch distance");
 constexpr int kProducerTid = CL4_SWEEP_PRODUCER;  // the thread that issues the TMA loads
 constexpr int kStageBytes = kBox * kBox * 4;    // 25600
 constexpr size_t kSweepSmem = (size_t)kStages * kStageBytes + 128;
@@ -118,7 +123,7 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
         ++p_item;
     };
     if (tid == kProducerTid) {
-        for (int i = 0; i < kStages - 1 && p_item < total; ++i) issue_next();
+        for (int i = 0; i < kAhead && p_item < total; ++i) issue_next();
     }
 
     float w[kPx][P];

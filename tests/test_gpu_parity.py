@@ -115,6 +115,27 @@ def test_pamr_small_map_paths_agree(cl4, oracle, monkeypatch, path, B, C, H, W, 
     np.testing.assert_allclose(got, oracle.pamr(x, m, T, dil), rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("mode", ["lattice", "nolattice"])
+@pytest.mark.parametrize("B,C,H,W,T", [
+    (2, 21, 96, 80, 10),     # partial tiles in x, 3 x 3 tiles
+    (2, 3, 50, 72, 10),      # partial tiles in both dimensions
+    (1, 2, 200, 36, 5),      # tall and narrow: many tile rows per CTA
+    (3, 2, 68, 132, 4),      # more tiles than one wave of classes; staggered class phase
+    (1, 1, 72, 68, 1),       # single class, single iteration: straight to the output
+    (5, 30, 160, 160, 2),    # 125 tiles x 30 classes: every CTA switches tiles (weight reload on the fly)
+])
+def test_pamr_lattice_sweep(cl4, oracle, monkeypatch, mode, B, C, H, W, T):
+    """The two-group lattice sweep (pamr_lattice.cu) and the 4-pixel TMA sweep on the class-default dilation set
+    (wss/modules.py:125), each against the oracle."""
+    monkeypatch.setenv("CL4_SWEEP", mode)
+    dil = [1, 2, 4, 8, 12, 24]
+    rng = np.random.default_rng(B * 1000 + C * 100 + H + W)
+    x = (rng.integers(0, 256, (B, 3, H, W)) / 255.0).astype(np.float32)
+    m = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).softmax(1).numpy()
+    got = cl4.PAMR(T, dil).cuda()(cuda(x), cuda(m)).cpu().numpy()
+    np.testing.assert_allclose(got, oracle.pamr(x, m, T, dil), rtol=RTOL, atol=ATOL)
+
+
 def test_pamr_fused_odd_width_and_resize(cl4, oracle):
     """The fused path has no W % 4 requirement and composes with the bilinear resize of :134."""
     rng = np.random.default_rng(11)
