@@ -48,6 +48,11 @@ SIGNATURES = {
     "cl4_contours8": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cl4_refine_labels": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, ctypes.c_double, _int, _flt, _int, _int,
                                  ctypes.c_longlong, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _sz, _vp]),
+    "cl4_denorm": (_int, [_vp, _vp, _int, _int, ctypes.c_longlong, ctypes.POINTER(_flt), ctypes.POINTER(_flt), _vp]),
+    "cl4_denorm_resize_ac": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, ctypes.POINTER(_flt),
+                                    ctypes.POINTER(_flt), _vp]),
+    "cl4_softmax_channels": (_int, [_vp, _vp, _int, _int, ctypes.c_longlong, _vp]),
+    "cl4_pseudo_gtmask": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _flt, _flt, _flt, _int, _vp]),
     "cl4_group_pixels": (_int, [_vp, _vp, _int, _int, _vp, _vp, _vp, _int, _int, _int, _int, _vp]),
 }
 
@@ -98,6 +103,10 @@ def ptr(t):
 
 def stream_ptr(device=None):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def float_array(values):
+    return (ctypes.c_float * len(values))(*[float(v) for v in values])
 
 
 def int_array(values):

@@ -35,6 +35,9 @@ namespace cl4 {
 #ifndef CL4_SWEEP_AHEAD
 #define CL4_SWEEP_AHEAD (CL4_SWEEP_STAGES - 1)
 #endif
+#ifndef CL4_SWEEP_L2_AHEAD
+#define CL4_SWEEP_L2_AHEAD 0
+#endif
 constexpr int kStages = CL4_SWEEP_STAGES;
 constexpr int kAhead = CL4_SWEEP_AHEAD;  // windows in flight beyond the current item (< kStages)
 static_assert(kAhead >= 1 && kAhead < kStages, "prefetch distance");
@@ -121,6 +124,16 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
         mbar_arrive_expect_tx(&full[s], kStageBytes);
         tma_load_3d(stage0 + (size_t)s * (kBox * kBox), &tmap, &full[s], ptc.x0, ptc.y0, ptc.b * C + pc);
         ++p_item;
+#if CL4_SWEEP_L2_AHEAD > 0  // pull a window further ahead into L2 (no shared memory needed for it)
+        if (p_item + CL4_SWEEP_L2_AHEAD - 1 < total) {
+            const int v2 = p_item + CL4_SWEEP_L2_AHEAD - 1 + s0;
+            int qk = v2 / C;
+            const int qc = v2 - qk * C;
+            if (qk >= n_my) qk -= n_my;
+            const TileCoord qtc = tile_coord(blockIdx.x + qk * gridDim.x, tiles_x, tiles_per_img);
+            tma_prefetch_l2_3d(&tmap, qtc.x0, qtc.y0, qtc.b * C + qc);
+        }
+#endif
     };
     if (tid == kProducerTid) {
         for (int i = 0; i < kAhead && p_item < total; ++i) issue_next();

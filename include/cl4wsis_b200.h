@@ -203,6 +203,29 @@ int cl4_refine_labels(const float* seg_logits, const float* center, const float*
                       float* out_center, float* out_offset, float* out_weight, int* status_out, int B, int C,
                       int H, int W, void* scratch, size_t scratch_bytes, cl4_stream_t stream);
 
+/* ------------------------------------------------------------------------- *
+ * Producers and consumers of PAMR inside the phase-1 step (train.py:372-385), SURVEY 8f rank 2.
+ *
+ * cl4_denorm: utils/utils.py:26-41 -- out = x * std[k] + mean[k] per RGB channel (two roundings, as
+ *   Tensor.mul_().add_()); images [planes = B*3][HW].  mean, std: HOST arrays of three floats.
+ * cl4_denorm_resize_ac: denorm followed by F.interpolate(..., (h, w), "bilinear", align_corners=True)
+ *   (train.py:376-378) in one pass; images [B,K,Hi,Wi] -> out [B,K,h,w].  mean == std == NULL: resize only.
+ * cl4_softmax_channels: int_masks.softmax(dim=1) (train.py:372-373); x, out [B,C,HW].
+ * cl4_pseudo_gtmask: `int_masks_soft[:, 1:] *= l1h[:, :, None, None]` (train.py:382; labels [B,C-1], NULL = no
+ *   gating; the gated mask goes to gated_out [B,C,HW], which may alias mask) followed by
+ *   wss/single_stage.py:18-40: per (b, c) plane maximum, scaled by cutoff_bkg (c = 0) / cutoff_top, floored at
+ *   cutoff_low; pseudo_out = (mask > threshold) as 0/1 floats, pixels claimed by more than one class cleared
+ *   when `ambiguous`.  thr_scratch: B*C floats.
+ * ------------------------------------------------------------------------- */
+int cl4_denorm(const float* images, float* out, int planes, int K, long long HW, const float* mean, const float* std,
+               cl4_stream_t stream);
+int cl4_denorm_resize_ac(const float* images, float* out, int B, int K, int Hi, int Wi, int h, int w, const float* mean,
+                         const float* std, cl4_stream_t stream);
+int cl4_softmax_channels(const float* x, float* out, int B, int C, long long HW, cl4_stream_t stream);
+int cl4_pseudo_gtmask(const float* mask, const float* labels, float* gated_out, float* pseudo_out, float* thr_scratch,
+                      int B, int C, int HW, float cutoff_top, float cutoff_bkg, float cutoff_low, int ambiguous,
+                      cl4_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -589,3 +589,57 @@ def test_get_ins_map_golden(cl4, golden_more, ci):
     assert pm.shape == shape and pm.dtype == np.bool_ and np.array_equal(pm, want_mask)
     np.testing.assert_allclose(ps, g[k + "pred_score"], rtol=2e-6, atol=0)
     assert np.array_equal(out["offset"].cpu().numpy(), g[k + "offset_after"])  # rescaled in place, as the reference
+
+
+# --------------------------------------------------------------------------- phase-1 producers / consumers of PAMR
+@pytest.mark.parametrize("name", ["p1_one", "p1_rect", "p1_same", "p1_voc"])
+def test_phase1_pieces_match_reference(cl4, golden_more, name):
+    """denorm, denorm + bilinear shrink, class softmax, label gating + pseudo_gtmask (train.py:372-385) against the
+    reference's own outputs; thresholded outputs bit-exact on identical inputs."""
+    from cl4wsis_b200.utils import denorm
+    from cl4wsis_b200.wss import single_stage as ss
+    g = golden_more("phase1")
+    k = lambda s: g[f"{name}__{s}"]  # noqa: E731
+    assert np.array_equal(denorm(cuda(k("img"))).cpu().numpy(), k("denorm"))
+    im = ss.denorm_resize(cuda(k("img")), k("im").shape[-2:]).cpu().numpy()
+    np.testing.assert_allclose(im, k("im"), rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(ss.softmax_channels(cuda(k("logits"))).cpu().numpy(), k("soft"), rtol=2e-6, atol=1e-9)
+    assert np.array_equal(ss.pseudo_gtmask(cuda(k("soft")), ambiguous=False).cpu().numpy(), k("pseudo_noamb"))
+    # gating + thresholds on the reference's PAMR output: bit-exact
+    lib, L = cl4._lib.load(), cl4._lib
+    pam = cuda(k("pamr").copy())
+    B, C, h, w = pam.shape
+    pseudo, thr = torch.empty_like(pam), torch.empty((B, C), device="cuda")
+    L.check(lib.cl4_pseudo_gtmask(L.ptr(pam), L.ptr(cuda(k("l1h"))), L.ptr(pam), L.ptr(pseudo), L.ptr(thr), B, C, h * w,
+                                  0.6, 0.7, 0.2, 1, L.stream_ptr()), "pseudo_gtmask")
+    assert np.array_equal(pam.cpu().numpy(), k("gated"))
+    assert np.array_equal(pseudo.cpu().numpy(), k("pseudo"))
+
+
+@pytest.mark.parametrize("name", ["p1_rect", "p1_voc"])
+def test_phase1_fused_step(cl4, golden_more, name):
+    """The whole of train.py:372-385 through phase1_pseudo_labels (softmax, denorm + shrink, PAMR with the trainer's
+    five dilations, gating, pseudo_gtmask).  The refined masks match to PAMR's tolerance; a pseudo-label may only
+    differ where the reference's own mask sits within that tolerance of its threshold."""
+    from cl4wsis_b200.wss import single_stage as ss
+    g = golden_more("phase1")
+    k = lambda s: g[f"{name}__{s}"]  # noqa: E731
+    pamr = cl4.PAMR(num_iter=10, dilations=[1, 2, 4, 8, 12]).cuda()
+    soft, pseudo = ss.phase1_pseudo_labels(cuda(k("img")), cuda(k("logits")), cuda(k("l1h")), pamr)
+    np.testing.assert_allclose(soft.cpu().numpy(), k("gated"), rtol=RTOL, atol=ATOL)
+    ref = k("gated")
+    B, C = ref.shape[:2]
+    mx = ref.reshape(B, C, -1).max(-1)
+    thr = np.maximum(mx * np.where(np.arange(C) == 0, np.float32(0.7), np.float32(0.6))[None, :], np.float32(0.2))[:, :, None, None]
+    near = np.abs(ref - thr) <= 2e-4 * np.abs(thr) + 2e-6
+    near_px = near.any(axis=1, keepdims=True)  # the ambiguity rule couples the classes of a pixel
+    diff = pseudo.cpu().numpy() != k("pseudo")
+    assert not (diff & ~near_px).any(), int((diff & ~near_px).sum())
+
+
+def test_phase1_error_behaviour(cl4):
+    from cl4wsis_b200.utils import denorm
+    with pytest.raises(AssertionError):
+        denorm(torch.zeros(2, 4, 8, 8, device="cuda"))           # utils/utils.py:35 "Expected RGB image"
+    with pytest.raises(RuntimeError):
+        denorm(torch.zeros(2, 3, 8, 8))                           # CPU tensor: no fallback

@@ -161,3 +161,22 @@ def test_smoothing_and_pseudo_label_generation_match_reference(golden_more, orac
         c, o, w, n = oracle.labelgen.pseudo_label_generation(g[k + "gt"], pts, g[k + "label"], g[k + "center"].shape[0], sigma, gg)
         assert n == int(g[k + "match"])
         assert np.array_equal(c, g[k + "center"]) and np.array_equal(o, g[k + "offset"]) and np.array_equal(w, g[k + "weight"])
+
+
+# --------------------------------------------------------------------------- phase-1 producers / consumers of PAMR
+P1_CASES = ["p1_one", "p1_rect", "p1_same", "p1_voc"]
+
+
+@pytest.mark.parametrize("name", P1_CASES)
+def test_phase1_oracle_matches_reference(golden_more, name):
+    """oracle/phase1.py against the reference's own denorm / interpolate / softmax / pseudo_gtmask outputs
+    (tests/golden/make_golden_more.py, section phase1)."""
+    from oracle import phase1 as p1
+    g = golden_more("phase1")
+    k = lambda s: g[f"{name}__{s}"]  # noqa: E731
+    assert np.array_equal(p1.denorm(k("img")), k("denorm"))                      # two rounded operations: bit-exact
+    np.testing.assert_allclose(p1.resize_bilinear_ac(k("denorm"), k("im").shape[-2:]), k("im"), rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(p1.softmax_channels(k("logits")), k("soft"), rtol=2e-6, atol=1e-9)
+    assert np.array_equal(p1.gate_labels(k("pamr"), k("l1h")), k("gated"))
+    assert np.array_equal(p1.pseudo_gtmask(k("gated"), True, 0.6, 0.7, 0.2), k("pseudo"))
+    assert np.array_equal(p1.pseudo_gtmask(k("soft"), False), k("pseudo_noamb"))
