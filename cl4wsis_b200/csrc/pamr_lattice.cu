@@ -305,7 +305,9 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const CUtens
         const int pb = item % kLParts, pj = pb * 4 + ((tid >> 5) & 3);
         float* pp = cx.part + pb * kLPartFloats + pbase;
         if (G == 0) {
+#ifndef CL4_LATTICE_NOHANDOVER  // ablation: free-running groups (wrong results)
             if (item >= kLParts) mbar_wait(&cx.pempty[pj], (uint32_t)((item / kLParts - 1) & 1));
+#endif
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -313,7 +315,9 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const CUtens
             __syncwarp();
             if (lane == 0) mbar_arrive(&cx.pfull[pj]);
         } else {
+#ifndef CL4_LATTICE_NOHANDOVER
             mbar_wait(&cx.pfull[pj], (uint32_t)((item / kLParts) & 1));
+#endif
             float* oc = o + (long long)c * out.plane;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -373,6 +377,9 @@ pamr_sweep_lattice_kernel(const __grid_constant__ CUtensorMap tmap, const float*
     }
     __syncthreads();
 
+#ifdef CL4_LATTICE_ONLY  // ablation: only one group runs (needs NOTMA + NOHANDOVER)
+    if ((threadIdx.x < kLGroupThreads) != (CL4_LATTICE_ONLY == 0)) return;
+#endif
     if (threadIdx.x < kLGroupThreads) lattice_group<0>(cx, &tmap, out);  // warp-uniform
     else lattice_group<1>(cx, &tmap, out);
 }
