@@ -37,19 +37,16 @@
 namespace cl4 {
 
 #ifndef CL4_LATTICE_STAGES
-#define CL4_LATTICE_STAGES 6
-#endif
-#ifndef CL4_LATTICE_AHEAD
-#define CL4_LATTICE_AHEAD 2
+#define CL4_LATTICE_STAGES 5
 #endif
 
-constexpr int kLThreads = 256;                       // 8 warps: 0-3 group A, 4-7 group B
+constexpr int kLThreads = 256;                       // 8 compute warps: 0-3 group A, 4-7 group B
+constexpr int kLLaunchThreads = kLThreads + 128;     // + a producer warpgroup (its first thread feeds the TMA ring)
 constexpr int kLGroupThreads = 128;
 constexpr int kLPitch = 84;                          // window pitch in floats; 84 % 32 == 20
 constexpr int kLStageFloats = kBox * kLPitch;        // 80 rows x 84 columns = 6720
 constexpr int kLStageBytes = kLStageFloats * 4;      // 26880 = 210 * 128
 constexpr int kLStages = CL4_LATTICE_STAGES;
-constexpr int kLAhead = CL4_LATTICE_AHEAD;           // items in flight beyond the current one
 constexpr int kLPartPitch = 36;                      // partial sums of group A: 32 rows x 36 floats (36 % 32 == 4)
 constexpr int kLPartFloats = kTile * kLPartPitch;    // 1152
 constexpr int kLPx = 8;                              // pixels per thread
@@ -59,13 +56,8 @@ constexpr int kLWeightsPerTile = kLW * kLThreads;    // 49152 floats = 48 taps x
 #ifndef CL4_LATTICE_PARTS
 #define CL4_LATTICE_PARTS 4
 #endif
-#ifndef CL4_LATTICE_PRODUCER
-#define CL4_LATTICE_PRODUCER 0
-#endif
-constexpr int kLProducerGroup = CL4_LATTICE_PRODUCER;  // which group's first thread issues the TMA loads
 constexpr int kLParts = CL4_LATTICE_PARTS;           // partial-sum buffers: how far group A may run ahead of group B
 constexpr size_t kLSmem = (size_t)kLStages * kLStageBytes + kLParts * kLPartFloats * 4 + (2 * kLStages + 8 * kLParts) * 8 + 64;
-static_assert(kLAhead >= 1 && kLAhead < kLStages, "prefetch distance");
 
 // ---- who owns pixel (y, x) of a tile in each group: thread (0..127 within the group) and slot (0..7) ----
 struct Owner {
@@ -192,10 +184,29 @@ __device__ __forceinline__ LTile ltile(int t, int tiles_x, int tiles_per_img) {
     return tc;
 }
 
+// The producer: one thread of a third warpgroup walks the items of this CTA in order, waits until all eight compute
+// warps have released the stage it is about to refill, and issues the window's TMA box.  The compute groups never
+// wait for one another through the ring.  (With the producer inside a compute warp the ring depth seen by the
+// leading group collapses and random CTAs ran whole launches 1.75x slower -- profiles/r01c_notes.md.)
+__device__ __forceinline__ void lattice_producer(const LatticeCtx& cx, const CUtensorMap* tmap) {
+    const int C = cx.C;
+    for (int p_item = 0; p_item < cx.total; ++p_item) {
+        const int s = p_item % kLStages;
+        if (p_item >= kLStages) mbar_wait(&cx.empty[s], (uint32_t)((p_item / kLStages - 1) & 1));
+        const int v = p_item + cx.s0;
+        int pk = v / C;
+        const int pc = v - pk * C;
+        if (pk == cx.n_my) pk = 0;
+        const LTile ptc = ltile(blockIdx.x + pk * gridDim.x, cx.tiles_x, cx.tiles_per_img);
+        mbar_arrive_expect_tx(&cx.full[s], kLStageBytes);
+        tma_load_3d(cx.stage0 + (size_t)s * kLStageFloats, tmap, &cx.full[s], ptc.x0, ptc.y0, ptc.b * C + pc);
+    }
+}
+
 // The item loop of one warp group (G = 0: A, G = 1: B).  Item i of this CTA is (tile ordinal, class) =
 // ((i + s0) / C mod n_my, (i + s0) mod C) as in pamr_tma.cu (staggered class phase).
 template <int G>
-__device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const CUtensorMap* tmap, const LatticeOut& out) {
+__device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const LatticeOut& out) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int tg = tid - G * kLGroupThreads;
     const int C = cx.C;
@@ -212,36 +223,6 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const CUtens
     }
     const int tb = (ry + kHalo) * kLPitch + rx + kHalo;  // window offset of the block origin
     const int pbase = ry * kLPartPitch + rx;             // partial-buffer offset
-
-    // ---- producer: the first thread of group kLProducerGroup issues the TMA loads.  It never waits for a stage
-    // it does not need yet (non-blocking test of the empty barrier, up to kLAhead items beyond the current one)
-    // and only blocks for the current item's own window.  Measured at B16 C21 512^2 (ms per sweep incl. frame):
-    //   producer in A, 6 stages, 5 ahead: 0.80-0.83 -- group A runs up to kLParts items ahead of B, the ring depth
-    //     seen by A collapses, and random CTAs stay 1.75x slower for a whole launch (bistable; not seen under ncu);
-    //   producer in A, 2 ahead: 0.66, no slow CTAs (the default);  producer in B, 5 ahead: 0.73, A waits on `full`;
-    //   blocking producer in A with a slack of 1 / 2 / 3 items behind the slowest warp: 1.09 / 0.71-0.77 / 0.62.
-    int p_item = 0;
-    auto issue_upto = [&](int item) {
-        while (p_item < cx.total && p_item <= item + kLAhead) {
-            const int s = p_item % kLStages;
-            if (p_item >= kLStages) {
-                const uint32_t parity = (uint32_t)((p_item / kLStages - 1) & 1);
-                if (p_item == item) mbar_wait(&cx.empty[s], parity);
-                else if (!mbar_test(&cx.empty[s], parity)) break;
-            }
-            const int v = p_item + cx.s0;
-            int pk = v / C;
-            const int pc = v - pk * C;
-            if (pk == cx.n_my) pk = 0;
-            const LTile ptc = ltile(blockIdx.x + pk * gridDim.x, cx.tiles_x, cx.tiles_per_img);
-            mbar_arrive_expect_tx(&cx.full[s], kLStageBytes);
-            tma_load_3d(cx.stage0 + (size_t)s * kLStageFloats, tmap, &cx.full[s], ptc.x0, ptc.y0, ptc.b * C + pc);
-            ++p_item;
-        }
-    };
-#ifndef CL4_LATTICE_NOTMA
-    if (G == kLProducerGroup && tg == 0) issue_upto(0);
-#endif
 
     float w[kLW];
     float acc[kLPx];
@@ -275,9 +256,6 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const CUtens
     }
 
     for (int item = 0; item < cx.total; ++item) {
-#ifndef CL4_LATTICE_NOTMA  // ablation: compute on whatever the stages hold
-        if (G == kLProducerGroup && tg == 0) issue_upto(item);
-#endif
 
         const int s = item % kLStages;
         const float* sp = cx.stage0 + (size_t)s * kLStageFloats + tb;
@@ -342,7 +320,7 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const CUtens
     }
 }
 
-__global__ void __launch_bounds__(kLThreads, 1)
+__global__ void __launch_bounds__(kLLaunchThreads, 1)
 pamr_sweep_lattice_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wts, LatticeOut out, int C,
                           int H, int W, int tiles_x, int tiles_y, int n_tiles) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -367,7 +345,7 @@ pamr_sweep_lattice_kernel(const __grid_constant__ CUtensorMap tmap, const float*
         tma_prefetch_desc(&tmap);
         for (int s = 0; s < kLStages; ++s) {
             mbar_init(&cx.full[s], 1);
-            mbar_init(&cx.empty[s], kLThreads / 32);
+            mbar_init(&cx.empty[s], kLThreads / 32);  // the eight compute warps
         }
         for (int s = 0; s < 4 * kLParts; ++s) {
             mbar_init(&cx.pfull[s], 1);   // warp j of group A
@@ -377,11 +355,19 @@ pamr_sweep_lattice_kernel(const __grid_constant__ CUtensorMap tmap, const float*
     }
     __syncthreads();
 
+    if (threadIdx.x >= kLThreads) {  // producer warpgroup: hand its registers to the compute warps
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+#ifndef CL4_LATTICE_NOTMA  // ablation: compute on whatever the stages hold
+        if (threadIdx.x == kLThreads) lattice_producer(cx, &tmap);
+#endif
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
 #ifdef CL4_LATTICE_ONLY  // ablation: only one group runs (needs NOTMA + NOHANDOVER)
     if ((threadIdx.x < kLGroupThreads) != (CL4_LATTICE_ONLY == 0)) return;
 #endif
-    if (threadIdx.x < kLGroupThreads) lattice_group<0>(cx, &tmap, out);  // warp-uniform
-    else lattice_group<1>(cx, &tmap, out);
+    if (threadIdx.x < kLGroupThreads) lattice_group<0>(cx, out);  // warp-uniform
+    else lattice_group<1>(cx, out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -533,7 +519,7 @@ int launch_sweep_lattice(const float* w, const float* padded_in, float* out, int
         return CL4_ECUDA;
     }
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-    pamr_sweep_lattice_kernel<<<grid, kLThreads, kLSmem, s>>>(tmap, w, so, C, H, W, tiles_x, tiles_y, n_tiles);
+    pamr_sweep_lattice_kernel<<<grid, kLLaunchThreads, kLSmem, s>>>(tmap, w, so, C, H, W, tiles_x, tiles_y, n_tiles);
     return check_launch("pamr_sweep_lattice");
 }
 

@@ -19,6 +19,9 @@
 // tile's value right after its final use, which hides the 196 KB weight fetch.  The weights are
 // stored tile-major ([tile][p/4][32][32][4], written by the weights kernel): a thread's 192 weights
 // are 48 float4 loads at immediate offsets from one pointer.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "pamr_internal.cuh"
 #include "pamr_sweep.cuh"
@@ -43,6 +46,10 @@ constexpr int kAhead = CL4_SWEEP_AHEAD;  // windows in flight beyond the current
 static_assert(kAhead >= 1 && kAhead < kStages, "prefetch distance");
 constexpr int kProducerTid = CL4_SWEEP_PRODUCER;  // the thread that issues the TMA loads
 constexpr int kStageBytes = kBox * kBox * 4;    // 25600
+#ifndef CL4_EXP_BOXH
+#define CL4_EXP_BOXH kBox  // experiment: load only the first CL4_EXP_BOXH rows of each window (wrong results, timing only)
+#endif
+constexpr int kLoadBytes = kBox * CL4_EXP_BOXH * 4;
 constexpr size_t kSweepSmem = (size_t)kStages * kStageBytes + 128;
 
 struct TileCoord {
@@ -72,8 +79,19 @@ __device__ __forceinline__ size_t tiled_weight_index(size_t tile, int P, int p, 
     return ((tile * (size_t)(P / 4) + (size_t)(p >> 2)) * (kTile * kTile) + (size_t)row * kTile + col) * 4 + (p & 3);
 }
 
-template <int D, class DS>
-__global__ void __launch_bounds__(kSweepThreads, 1)
+#ifndef CL4_SWEEP_CTAS_SMALL_D
+#define CL4_SWEEP_CTAS_SMALL_D 1  // experiment: 2 = two CTAs per SM when D <= 3 (96 weight registers)
+#endif
+// kWS (warp-specialised): a third warpgroup (threads 256..383) only feeds the ring -- its first thread waits
+// for released stages and issues the TMA boxes -- and gives its registers to the eight compute warps through
+// setmaxnreg (24 / 240 per thread: 128*24 + 256*240 = 64512 registers).  The compute warps then never wait for
+// one another: with the producer inside compute warp 0 the whole CTA advances at the pace of that one warp.
+constexpr int kWsThreads = kSweepThreads + 128;
+#ifdef CL4_SWEEP_DEBUG  // per CTA: [0] total cycles, [1] producer cycles in empty waits, [2..9] cycles of warp w in full waits
+__device__ long long g_sweep_dbg[148 * 10];
+#endif
+template <int D, class DS, bool kWS>
+__global__ void __launch_bounds__(kWS ? kWsThreads : kSweepThreads, (D <= 3 && !kWS ? CL4_SWEEP_CTAS_SMALL_D : 1))
 pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wts, SweepOut out, int C,
                       int H, int W, int tiles_x, int tiles_y, int n_tiles, Dilations dil) {
     constexpr int P = 8 * D;
@@ -113,6 +131,9 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
     // ---- producer (thread 0 only): p_item is the next item to issue.  The padded plane holds pixel
     // (y, x) at (y + 24, x + 24), so the window of tile (y0, x0) starts at (y0, x0).
     int p_item = 0;
+#ifdef CL4_SWEEP_DEBUG
+    long long dbg_wait = 0, dbg_t0 = clock64();
+#endif
     auto issue_next = [&]() {
         const int v = p_item + s0;
         int pk = v / C;
@@ -120,9 +141,19 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
         if (pk == n_my) pk = 0;
         const TileCoord ptc = tile_coord(blockIdx.x + pk * gridDim.x, tiles_x, tiles_per_img);
         const int s = p_item % kStages;
+#ifdef CL4_SWEEP_DEBUG
+        const long long tw0 = clock64();
+#endif
         if (p_item >= kStages) mbar_wait(&empty[s], (uint32_t)((p_item / kStages - 1) & 1));
-        mbar_arrive_expect_tx(&full[s], kStageBytes);
+#ifdef CL4_SWEEP_DEBUG
+        dbg_wait += clock64() - tw0;
+#endif
+#ifdef CL4_EXP_NOLOAD  // experiment: the handshake without the copy
+        mbar_arrive(&full[s]);
+#else
+        mbar_arrive_expect_tx(&full[s], kLoadBytes);
         tma_load_3d(stage0 + (size_t)s * (kBox * kBox), &tmap, &full[s], ptc.x0, ptc.y0, ptc.b * C + pc);
+#endif
         ++p_item;
 #if CL4_SWEEP_L2_AHEAD > 0  // pull a window further ahead into L2 (no shared memory needed for it)
         if (p_item + CL4_SWEEP_L2_AHEAD - 1 < total) {
@@ -135,7 +166,19 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
         }
 #endif
     };
-    if (tid == kProducerTid) {
+    if (kWS) {
+        if (tid >= kSweepThreads) {  // producer warpgroup
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+            if (tid == kSweepThreads) {
+                while (p_item < total) issue_next();  // blocks on the empty barrier of the stage it refills
+#ifdef CL4_SWEEP_DEBUG
+                if (blockIdx.x < 148) g_sweep_dbg[blockIdx.x * 10 + 1] = dbg_wait;
+#endif
+            }
+            return;
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+    } else if (tid == kProducerTid) {
         for (int i = 0; i < kAhead && p_item < total; ++i) issue_next();
     }
 
@@ -188,7 +231,7 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
     }
 
     for (int item = 0; item < total; ++item) {
-        if (tid == kProducerTid && p_item < total) issue_next();  // refills the stage released by item-1
+        if (!kWS && tid == kProducerTid && p_item < total) issue_next();  // refills the stage released by item-1
 
         const int s = item % kStages;
         const float* sp = stage0 + (size_t)s * (kBox * kBox) + sbase;
@@ -196,7 +239,15 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
         if (nk == n_my) nk = 0;
         // last class of this tile visit and another tile follows: refill the weights on the fly
         const bool reload = (c == C - 1) && (item + 1 < total) && (nk != k);
+#ifdef CL4_SWEEP_DEBUG
+        const long long tf0 = clock64();
+#endif
+#ifndef CL4_EXP_NOWAITFULL  // experiment: consumers do not wait for the window (racy, timing only)
         mbar_wait(&full[s], (uint32_t)((item / kStages) & 1));
+#endif
+#ifdef CL4_SWEEP_DEBUG
+        if (kWS) dbg_wait += clock64() - tf0;
+#endif
 
         if (reload)
             sweep_class<D, DS, true>(w, sp, dil, weight_ptr(blockIdx.x + nk * gridDim.x), acc);
@@ -219,6 +270,12 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
             }
         }
     }
+#ifdef CL4_SWEEP_DEBUG
+    if (kWS && lane == 0 && blockIdx.x < 148) {
+        g_sweep_dbg[blockIdx.x * 10 + 2 + wrp] = dbg_wait;
+        if (wrp == 0) g_sweep_dbg[blockIdx.x * 10] = clock64() - dbg_t0;
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -483,18 +540,32 @@ int launch_weights_tma(const float* padded_img, float* w, int B, int K, int H, i
     return CL4_EUNSUPPORTED;
 }
 
-template <int D, class DS>
-static int launch_one(const CUtensorMap& tmap, const float* w, const SweepOut& out, int C, int H, int W, int tiles_x,
-                      int tiles_y, int n_tiles, const Dilations& dil, cudaStream_t s) {
-    auto kern = pamr_sweep_tma_kernel<D, DS>;
+template <int D, class DS, bool kWS>
+static int launch_one_ws(const CUtensorMap& tmap, const float* w, const SweepOut& out, int C, int H, int W, int tiles_x,
+                         int tiles_y, int n_tiles, const Dilations& dil, cudaStream_t s) {
+    auto kern = pamr_sweep_tma_kernel<D, DS, kWS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem);  // per device
     if (e != cudaSuccess) {
         set_error("pamr_sweep_tma: smem attribute: %s", cudaGetErrorString(e));
         return CL4_ECUDA;
     }
-    const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-    kern<<<grid, kSweepThreads, kSweepSmem, s>>>(tmap, w, out, C, H, W, tiles_x, tiles_y, n_tiles, dil);
+    const int ctas = kNumSMs * (D <= 3 ? CL4_SWEEP_CTAS_SMALL_D : 1);
+    const int grid = n_tiles < ctas ? n_tiles : ctas;
+    kern<<<grid, kWS ? kWsThreads : kSweepThreads, kSweepSmem, s>>>(tmap, w, out, C, H, W, tiles_x, tiles_y, n_tiles, dil);
     return check_launch("pamr_sweep_tma");
+}
+
+// CL4_SWEEP=ws / nows selects the warp-specialised / the in-warp producer (default: CL4_SWEEP_WS_DEFAULT)
+#ifndef CL4_SWEEP_WS_DEFAULT
+#define CL4_SWEEP_WS_DEFAULT 0
+#endif
+template <int D, class DS>
+static int launch_one(const CUtensorMap& tmap, const float* w, const SweepOut& out, int C, int H, int W, int tiles_x,
+                      int tiles_y, int n_tiles, const Dilations& dil, cudaStream_t s) {
+    const char* f = getenv("CL4_SWEEP");
+    const bool ws = f ? (strcmp(f, "ws") == 0 || (strcmp(f, "nows") != 0 && CL4_SWEEP_WS_DEFAULT)) : CL4_SWEEP_WS_DEFAULT;
+    if (ws && D >= 4) return launch_one_ws<D, DS, true>(tmap, w, out, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
+    return launch_one_ws<D, DS, false>(tmap, w, out, C, H, W, tiles_x, tiles_y, n_tiles, dil, s);
 }
 
 template <int D>
@@ -516,7 +587,7 @@ int launch_sweep_tma(const float* w, const float* padded_in, float* out, int out
                      const Dilations& dil, int D, cudaStream_t s) {
     CUtensorMap tmap;
     const int Wp = W + 2 * kHalo, Hp = H + 2 * kHalo;
-    const int rc = encode_tmap_3d_f32(&tmap, padded_in, Wp, Hp, (long long)B * C, kBox, kBox);
+    const int rc = encode_tmap_3d_f32(&tmap, padded_in, Wp, Hp, (long long)B * C, kBox, CL4_EXP_BOXH);
     if (rc != 0) {
         set_error("pamr_sweep_tma: cuTensorMapEncodeTiled failed (%d)", rc);
         return CL4_ECUDA;
@@ -546,3 +617,9 @@ int launch_sweep_tma(const float* w, const float* padded_in, float* out, int out
 }
 
 }  // namespace cl4
+
+#ifdef CL4_SWEEP_DEBUG
+extern "C" int cl4_debug_sweep_waits(long long* out1480) {
+    return (int)cudaMemcpyFromSymbol(out1480, cl4::g_sweep_dbg, sizeof(long long) * 1480);
+}
+#endif

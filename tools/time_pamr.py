@@ -6,7 +6,8 @@ import cl4wsis_b200 as cl4
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 21
 H = W = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 Bs = [int(b) for b in sys.argv[3:]] or [1, 2, 4, 16]
-T, dil = 10, [1, 2, 4, 8, 12, 24]
+T = 10
+dil = [int(d) for d in os.environ.get("DIL", "1,2,4,8,12,24").split(",")]
 for B in Bs:
     step = cl4.PseudoLabelStep(B, C, H, W, num_iter=T, dilations=dil)
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -24,4 +25,4 @@ for B in Bs:
     ms = sum(a.elapsed_time(b) for a, b in evs) / (n * T)
     tiles = B * ((H + 31) // 32) * ((W + 31) // 32)
     rounds = (tiles + 147) // 148
-    print(f"B={B:3d} C={C} {H}x{W}: {ms:.4f} ms per sweep(+frame); {rounds} tile rounds -> {ms * 1e-3 * 1.965e9 / (rounds * C):.0f} cycles per (tile, class) item")
+    print(f"dil={dil} B={B:3d} C={C} {H}x{W}: {ms:.4f} ms per sweep(+frame); {rounds} tile rounds -> {ms * 1e-3 * 1.965e9 / (rounds * C):.0f} cycles per (tile, class) item")
