@@ -27,8 +27,8 @@
 //           cp.async.bulk.tensor box into a ring of stages with full/empty mbarriers.  The pitch of
 //           84 floats (= 20 mod 32) makes group A's lane pattern (4 x 4 phases x 2 super-blocks)
 //           bank-conflict free; group B's half-warps read 16 adjacent float2.
-//   weights thread-major [tile][k = slot*24 + tap][thread] (written by pamr_weights_lattice_kernel),
-//           a warp's load of one k is one 128-byte run; same size as the 32x32 tile-major layout.
+//   weights thread-major [tile][k/4][thread] float4, k = slot*24 + tap (written by pamr_weights_lattice_kernel):
+//           48 128-bit loads per thread, a warp's load is one 512-byte run; same size as the 32x32 tile-major layout.
 #include "common.cuh"
 #include "pamr_internal.cuh"
 #include "pamr_sweep.cuh"
@@ -81,11 +81,24 @@ __host__ __device__ constexpr bool is_tap(int di, int dj, int s) {
     return (di == -s || di == 0 || di == s) && (dj == -s || dj == 0 || dj == s) && !(di == 0 && dj == 0);
 }
 
+// The thread's 192 weights of a tile: 48 float4 at [k/4][thread].
+__device__ __forceinline__ void load_weight_group(float (&w)[kLW], const float4* __restrict__ wp, const int g) {
+    const float4 v = __ldg(wp + g * kLThreads);
+    w[4 * g + 0] = v.x;
+    w[4 * g + 1] = v.y;
+    w[4 * g + 2] = v.z;
+    w[4 * g + 3] = v.w;
+}
+__device__ __forceinline__ void load_weights(float (&w)[kLW], const float4* __restrict__ wp) {
+#pragma unroll
+    for (int g = 0; g < kLW / 4; ++g) load_weight_group(w, wp, g);
+}
+
 // One source value `v` at lattice position (r, c) of an A x B block whose taps are the steps 1..NS of the
 // lattice: feed every (pixel, tap) that reads it.  Weight register of (pixel slot, step s, tap): slot*24 + (s-1)*8 + tap.
 template <int A, int B, int NS, bool kReload>
 __device__ __forceinline__ void feed(float (&w)[kLW], float (&acc)[kLPx], const float v, const int r, const int c,
-                                     const float* __restrict__ nw) {
+                                     const float4* __restrict__ nw) {
 #pragma unroll
     for (int i = 0; i < A; ++i)
 #pragma unroll
@@ -96,7 +109,9 @@ __device__ __forceinline__ void feed(float (&w)[kLW], float (&acc)[kLPx], const 
                 if (is_tap(di, dj, s)) {
                     const int k = (i * B + j) * kLTaps + (s - 1) * 8 + tap_index(di / s, dj / s);
                     acc[i * B + j] = fmaf(w[k], v, acc[i * B + j]);
-                    if (kReload) w[k] = __ldg(nw + k * kLThreads);
+                    // sources arrive in row-major order, so taps 3 and 7 are the last uses of their float4:
+                    // refill it with the next tile's weights right away (kReload: last class of a tile)
+                    if (kReload && (k & 3) == 3) load_weight_group(w, nw, k >> 2);
                 }
             }
 }
@@ -114,7 +129,7 @@ __host__ __device__ constexpr bool source_needed(int r, int c) {
 // pixel (0, 0) inside the window.  76 of the 8 x 10 lattice positions are read.
 template <bool kReload>
 __device__ __forceinline__ void group_a_class(float (&w)[kLW], float (&acc)[kLPx], const float* __restrict__ sp,
-                                              const float* __restrict__ nw) {
+                                              const float4* __restrict__ nw) {
 #pragma unroll
     for (int r = -3; r < 2 + 3; ++r)
 #pragma unroll
@@ -130,7 +145,7 @@ __device__ __forceinline__ void group_a_class(float (&w)[kLW], float (&acc)[kLPx
 // share one float2 per tap.
 template <bool kReload>
 __device__ __forceinline__ void group_b_class(float (&w)[kLW], float (&acc)[kLPx], const float* __restrict__ sp,
-                                              const float* __restrict__ nw) {
+                                              const float4* __restrict__ nw) {
 #pragma unroll
     for (int r = -2; r < 4 + 2; ++r)
 #pragma unroll
@@ -150,9 +165,9 @@ __device__ __forceinline__ void group_b_class(float (&w)[kLW], float (&acc)[kLPx
                 const int k0 = (i * 2) * kLTaps + 16 + tap_index(a, b), k1 = k0 + kLTaps;
                 acc[i * 2] = fmaf(w[k0], v.x, acc[i * 2]);
                 acc[i * 2 + 1] = fmaf(w[k1], v.y, acc[i * 2 + 1]);
-                if (kReload) {
-                    w[k0] = __ldg(nw + k0 * kLThreads);
-                    w[k1] = __ldg(nw + k1 * kLThreads);
+                if (kReload && (k0 & 3) == 3) {
+                    load_weight_group(w, nw, k0 >> 2);
+                    load_weight_group(w, nw, k1 >> 2);
                 }
             }
 }
@@ -192,7 +207,7 @@ __device__ __forceinline__ void lattice_producer(const LatticeCtx& cx, const CUt
     const int C = cx.C;
     for (int p_item = 0; p_item < cx.total; ++p_item) {
         const int s = p_item % kLStages;
-        if (p_item >= kLStages) mbar_wait(&cx.empty[s], (uint32_t)((p_item / kLStages - 1) & 1));
+        if (p_item >= kLStages) mbar_wait_relaxed(&cx.empty[s], (uint32_t)((p_item / kLStages - 1) & 1));
         const int v = p_item + cx.s0;
         int pk = v / C;
         const int pc = v - pk * C;
@@ -226,7 +241,9 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
 
     float w[kLW];
     float acc[kLPx];
-    auto weight_ptr = [&](int t) -> const float* { return cx.wts + (size_t)t * kLWeightsPerTile + tid; };
+    auto weight_ptr = [&](int t) -> const float4* {
+        return reinterpret_cast<const float4*>(cx.wts + (size_t)t * kLWeightsPerTile) + tid;
+    };
     auto prefetch_next_weights = [&](int kk) {
         int nn = kk + 1;
         if (nn == cx.n_my) nn = 0;
@@ -250,9 +267,7 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
     if (cx.total > 0) {
         enter_tile(0);
         prefetch_next_weights(0);
-        const float* wp = weight_ptr(blockIdx.x);
-#pragma unroll
-        for (int i = 0; i < kLW; ++i) w[i] = __ldg(wp + i * kLThreads);
+        load_weights(w, weight_ptr(blockIdx.x));
     }
 
     for (int item = 0; item < cx.total; ++item) {
@@ -262,7 +277,7 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
         int nk = k + 1;
         if (nk == cx.n_my) nk = 0;
         const bool reload = (c == C - 1) && (item + 1 < cx.total) && (nk != k);
-        const float* nw = weight_ptr(blockIdx.x + nk * gridDim.x);
+        const float4* nw = weight_ptr(blockIdx.x + nk * gridDim.x);
 #ifndef CL4_LATTICE_NOTMA
         mbar_wait(&cx.full[s], (uint32_t)((item / kLStages) & 1));
 #endif
@@ -448,14 +463,17 @@ pamr_weights_lattice_kernel(const __grid_constant__ CUtensorMap tmap, float* __r
         const float rz = 1.f / z;
         // group A holds dilations 4, 8, 12 (taps 16..39), group B dilations 1, 2 (taps 0..15) and 24 (taps 40..47)
         const Owner oa = owner_a(y, x), ob = owner_b(y, x);
-        float* pa = o + (size_t)(oa.slot * kLTaps) * kLThreads + oa.thread;
-        float* pb = o + (size_t)(ob.slot * kLTaps) * kLThreads + kLGroupThreads + ob.thread;
+        float4* pa = reinterpret_cast<float4*>(o) + (size_t)(oa.slot * (kLTaps / 4)) * kLThreads + oa.thread;
+        float4* pb = reinterpret_cast<float4*>(o) + (size_t)(ob.slot * (kLTaps / 4)) * kLThreads + kLGroupThreads + ob.thread;
 #pragma unroll
-        for (int t = 0; t < 24; ++t) pa[t * kLThreads] = logit[16 + t] * rz;
+        for (int q = 0; q < 6; ++q)
+            pa[q * kLThreads] = make_float4(logit[16 + 4 * q] * rz, logit[17 + 4 * q] * rz, logit[18 + 4 * q] * rz, logit[19 + 4 * q] * rz);
 #pragma unroll
-        for (int t = 0; t < 16; ++t) pb[t * kLThreads] = logit[t] * rz;
+        for (int q = 0; q < 4; ++q)
+            pb[q * kLThreads] = make_float4(logit[4 * q] * rz, logit[4 * q + 1] * rz, logit[4 * q + 2] * rz, logit[4 * q + 3] * rz);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) pb[(16 + t) * kLThreads] = logit[40 + t] * rz;
+        for (int q = 0; q < 2; ++q)
+            pb[(4 + q) * kLThreads] = make_float4(logit[40 + 4 * q] * rz, logit[41 + 4 * q] * rz, logit[42 + 4 * q] * rz, logit[43 + 4 * q] * rz);
     }
 }
 
