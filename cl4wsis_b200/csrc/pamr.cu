@@ -15,7 +15,7 @@
 #include "pamr_internal.cuh"
 
 #ifndef CL4_LATTICE_DEFAULT
-#define CL4_LATTICE_DEFAULT 0
+#define CL4_LATTICE_DEFAULT 1
 #endif
 
 namespace cl4 {
@@ -321,7 +321,7 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
     float* bufB = reinterpret_cast<float*>(base + wbytes + padded);
     // CL4_SWEEP=v1 forces the register/L1 kernel, CL4_SWEEP=tma skips the fused small-map kernel
     // (A/B timing and tests of the other paths)
-    // CL4_SWEEP=lattice / nolattice: take / skip the lattice sweep wherever it applies
+    // CL4_SWEEP=lattice / nolattice: take / skip the lattice sweep (pamr_lattice.cu; the default wherever it applies)
     const char* force = getenv("CL4_SWEEP");
     const bool force_v1 = force && strcmp(force, "v1") == 0, force_tma = force && strcmp(force, "tma") == 0;
     const bool force_lat = force && strcmp(force, "lattice") == 0, no_lat = force && strcmp(force, "nolattice") == 0;

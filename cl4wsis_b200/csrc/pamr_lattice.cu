@@ -56,6 +56,10 @@ constexpr int kLWeightsPerTile = kLW * kLThreads;    // 49152 floats = 48 taps x
 #ifndef CL4_LATTICE_PARTS
 #define CL4_LATTICE_PARTS 4
 #endif
+#ifndef CL4_LATTICE_FINISHER
+#define CL4_LATTICE_FINISHER 1
+#endif
+constexpr int kLFin = CL4_LATTICE_FINISHER;          // the group that adds the other's partial sums and stores (0: A, 1: B)
 constexpr int kLParts = CL4_LATTICE_PARTS;           // partial-sum buffers: how far group A may run ahead of group B
 constexpr size_t kLSmem = (size_t)kLStages * kLStageBytes + kLParts * kLPartFloats * 4 + (2 * kLStages + 8 * kLParts) * 8 + 64;
 
@@ -254,14 +258,24 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
     };
 
     int k = 0, c = cx.s0;
-    // group B finishes the pixels: store pointer and the number of valid rows of its 4 x 2 block
+    // the finishing group stores the pixels: store pointer and validity of its pixels (B: number of valid rows of
+    // its 4 x 2 block; A: one bit per pixel of its 2 x 4 lattice block)
     float* o = nullptr;
     int nrows = 0;
     auto enter_tile = [&](int kk) {
-        if (G != 1) return;
+        if (G != kLFin) return;
         const LTile tc = ltile(blockIdx.x + kk * gridDim.x, cx.tiles_x, cx.tiles_per_img);
         const int y = tc.y0 + ry, x = tc.x0 + rx;
-        nrows = (x < cx.W) ? min(max(cx.H - y, 0), 4) : 0;
+        if (G == 1) {
+            nrows = (x < cx.W) ? min(max(cx.H - y, 0), 4) : 0;
+        } else {
+            nrows = 0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (y + 4 * i < cx.H && x + 4 * j < cx.W) nrows |= 1 << (i * 4 + j);
+        }
         o = out.ptr + (long long)tc.b * C * out.plane + (long long)y * out.pitch + x;
     };
     if (cx.total > 0) {
@@ -270,16 +284,28 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
         load_weights(w, weight_ptr(blockIdx.x));
     }
 
-    for (int item = 0; item < cx.total; ++item) {
+    // loop state kept incrementally (no division per item): ring stage + phase, partial buffer + phase,
+    // window pointer, hand-over barrier of this warp pair
+    const uint32_t full0 = smem_u32(cx.full), empty0 = smem_u32(cx.empty);
+    const uint32_t pfull0 = smem_u32(cx.pfull) + 8u * ((tid >> 5) & 3), pempty0 = smem_u32(cx.pempty) + 8u * ((tid >> 5) & 3);
+    int stage = 0, pb = 0;
+    uint32_t full_phase = 0, part_phase = 0;
+    const float* sp = cx.stage0 + tb;
+    float* pp = cx.part + pbase;
+    float* oc = (G == kLFin) ? o + (long long)c * out.plane : nullptr;
 
-        const int s = item % kLStages;
-        const float* sp = cx.stage0 + (size_t)s * kLStageFloats + tb;
-        int nk = k + 1;
-        if (nk == cx.n_my) nk = 0;
-        const bool reload = (c == C - 1) && (item + 1 < cx.total) && (nk != k);
-        const float4* nw = weight_ptr(blockIdx.x + nk * gridDim.x);
+    for (int item = 0; item < cx.total; ++item) {
+        // last class of this tile visit and another tile follows: refill the weights on the fly
+        bool reload = false;
+        const float4* nw = nullptr;
+        int nk = k;
+        if (c == C - 1) {
+            nk = (k + 1 == cx.n_my) ? 0 : k + 1;
+            reload = (item + 1 < cx.total) && (nk != k);
+            nw = weight_ptr(blockIdx.x + nk * gridDim.x);
+        }
 #ifndef CL4_LATTICE_NOTMA
-        mbar_wait(&cx.full[s], (uint32_t)((item / kLStages) & 1));
+        mbar_wait_u32(full0 + 8u * stage, full_phase);
 #endif
 
 #pragma unroll
@@ -292,38 +318,64 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
             else group_b_class<false>(w, acc, sp, nw);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&cx.empty[s]);  // this warp no longer reads the window
+        if (lane == 0) mbar_arrive_u32(empty0 + 8u * stage);  // this warp no longer reads the window
 
         // A's warp j and B's warp j own the same 8 rows of the tile, so the hand-over is per warp pair
-        const int pb = item % kLParts, pj = pb * 4 + ((tid >> 5) & 3);
-        float* pp = cx.part + pb * kLPartFloats + pbase;
-        if (G == 0) {
+        if (G != kLFin) {
 #ifndef CL4_LATTICE_NOHANDOVER  // ablation: free-running groups (wrong results)
-            if (item >= kLParts) mbar_wait(&cx.pempty[pj], (uint32_t)((item / kLParts - 1) & 1));
+            if (item >= kLParts) mbar_wait_u32(pempty0 + 32u * pb, part_phase ^ 1u);
 #endif
+            if (G == 0) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+                for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) pp[i * 4 * kLPartPitch + j * 4] = acc[i * 4 + j];
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&cx.pfull[pj]);
-        } else {
-#ifndef CL4_LATTICE_NOHANDOVER
-            mbar_wait(&cx.pfull[pj], (uint32_t)((item / kLParts) & 1));
-#endif
-            float* oc = o + (long long)c * out.plane;
+                    for (int j = 0; j < 4; ++j) pp[i * 4 * kLPartPitch + j * 4] = acc[i * 4 + j];
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 a = *reinterpret_cast<const float2*>(pp + i * kLPartPitch);
-                float2 r;
-                r.x = acc[2 * i] + a.x;
-                r.y = acc[2 * i + 1] + a.y;
-                if (i < nrows) *reinterpret_cast<float2*>(oc + (long long)i * out.pitch) = r;
+                for (int i = 0; i < 4; ++i)
+                    *reinterpret_cast<float2*>(pp + i * kLPartPitch) = make_float2(acc[2 * i], acc[2 * i + 1]);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&cx.pempty[pj]);
+            if (lane == 0) mbar_arrive_u32(pfull0 + 32u * pb);
+        } else {
+#ifndef CL4_LATTICE_NOHANDOVER
+            mbar_wait_u32(pfull0 + 32u * pb, part_phase);
+#endif
+            if (G == 1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 a = *reinterpret_cast<const float2*>(pp + i * kLPartPitch);
+                    float2 r;
+                    r.x = acc[2 * i] + a.x;
+                    r.y = acc[2 * i + 1] + a.y;
+                    if (i < nrows) *reinterpret_cast<float2*>(oc + (long long)i * out.pitch) = r;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float r = acc[i * 4 + j] + pp[i * 4 * kLPartPitch + j * 4];
+                        if ((nrows >> (i * 4 + j)) & 1) oc[(long long)(4 * i) * out.pitch + 4 * j] = r;
+                    }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_u32(pempty0 + 32u * pb);
+            oc += out.plane;
         }
 
+        sp += kLStageFloats;
+        if (++stage == kLStages) {
+            stage = 0;
+            full_phase ^= 1u;
+            sp -= (size_t)kLStages * kLStageFloats;
+        }
+        pp += kLPartFloats;
+        if (++pb == kLParts) {
+            pb = 0;
+            part_phase ^= 1u;
+            pp -= kLParts * kLPartFloats;
+        }
         if (++c == C) {
             c = 0;
             if (nk != k) {
@@ -331,6 +383,7 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
                 enter_tile(k);
                 prefetch_next_weights(k);
             }
+            if (G == kLFin) oc = o;
         }
     }
 }
