@@ -359,11 +359,19 @@ def main():
     pamr_flops = 2.0 * C * P * T * H * W
     per_img_s = stats["elapsed_s"] / (B * K_)
     tiles = B * ((H + 31) // 32) * ((W + 31) // 32)
-    smem_bytes = tiles * C * (1024 * 143.0 + 80 * 80 * 4.0) if len(dil) == 6 else float("nan")
+    # shared-memory bytes one launch moves: LDS/STS of the compute warps + the TMA box per (tile, class)
+    lattice = dil == [1, 2, 4, 8, 12, 24] and os.environ.get("CL4_SWEEP") in (None, "", "lattice")
+    if lattice:    # group A 128 thr x (76 + 8) x 4 B, group B 128 thr x (56 + 4) x 8 B, window 80 x 84 fp32
+        smem_bytes = tiles * C * (128 * 84 * 4.0 + 128 * 60 * 8.0 + 80 * 84 * 4.0)
+    elif len(dil) == 6:
+        smem_bytes = tiles * C * (1024 * 143.0 + 80 * 80 * 4.0)
+    else:
+        smem_bytes = float("nan")
     sm_hz = (clk.get("sm_mhz") or 1965) * 1e6
     # dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch from the committed ncu --set full
-    # capture of this workload (profiles/r01b_sweep_ncu_raw.csv); other workloads were not captured
-    traffic = 1.892e9 if args.workload == "voc_b16_c21_512" else None
+    # capture of this workload (profiles/r01d_sweep_ncu_raw.csv: 1.540 GB read + 0.343 GB written by the lattice sweep;
+    # profiles/r01b_sweep_ncu_raw.csv: 1.892 GB for the 4-pixel sweep); other workloads were not captured
+    traffic = (1.883e9 if lattice else 1.892e9) if args.workload == "voc_b16_c21_512" else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
         "ms_per_step": 1e3 * stats["elapsed_s"] / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -371,7 +379,7 @@ def main():
         "config": {"workload": args.workload, "B_per_gpu": B, "C": C, "H": H, "W": W, "dilations": dil, "num_iter": T,
                    "nms_kernel": cfg["nms"], "threshold": cfg["thr"], "centres_per_image": cfg["Kc"],
                    "mask": "dense softmax over all classes", "l2": "inputs + scratch per step exceed L2 (no flush needed)"},
-        "roofline": {"bound": "hbm", "kernel": "pamr_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "pamr_sweep_lattice" if lattice else "pamr_sweep_tma", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": sweep_bytes, "mean_launch_ms": sweep_ms},
         "path_roofline": {"bytes_iter_frac_of_hbm": pamr_bytes_iter / per_img_s / 1e9 / peak,

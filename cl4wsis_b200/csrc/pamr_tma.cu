@@ -144,7 +144,10 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
 #ifdef CL4_SWEEP_DEBUG
         const long long tw0 = clock64();
 #endif
-        if (p_item >= kStages) mbar_wait(&empty[s], (uint32_t)((p_item / kStages - 1) & 1));
+        if (p_item >= kStages) {
+            if (kWS) mbar_wait_relaxed(&empty[s], (uint32_t)((p_item / kStages - 1) & 1));  // dedicated thread: no spinning
+            else mbar_wait(&empty[s], (uint32_t)((p_item / kStages - 1) & 1));
+        }
 #ifdef CL4_SWEEP_DEBUG
         dbg_wait += clock64() - tw0;
 #endif
@@ -557,7 +560,7 @@ static int launch_one_ws(const CUtensorMap& tmap, const float* w, const SweepOut
 
 // CL4_SWEEP=ws / nows selects the warp-specialised / the in-warp producer (default: CL4_SWEEP_WS_DEFAULT)
 #ifndef CL4_SWEEP_WS_DEFAULT
-#define CL4_SWEEP_WS_DEFAULT 0
+#define CL4_SWEEP_WS_DEFAULT 1
 #endif
 template <int D, class DS>
 static int launch_one(const CUtensorMap& tmap, const float* w, const SweepOut& out, int C, int H, int W, int tiles_x,
