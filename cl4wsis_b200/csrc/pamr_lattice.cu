@@ -17,11 +17,14 @@
 // 4*(76+8) + 4*(112+8) = 816 LDS/STS wavefronts (the 4-pixel kernel: 1144) + 210 of TMA writes.
 // Eight accumulators per thread also double the FMA-level parallelism.
 //
-// Status: opt-in (CL4_SWEEP=lattice), parity-tested, NOT the default.  It moves 27 % fewer shared-memory
-// wavefronts than the 4-pixel kernel (ncu: 72.1 M vs 98.5 M per launch) but is not faster (0.62-0.66 ms vs
-// 0.61 ms per sweep): without any TMA traffic its loop still takes 1430 cycles per (tile, class) against an
-// 816-wavefront floor, i.e. with 8 warps per SM (255 registers) the loop is bound by instruction latency and
-// by the hand-over between the groups, not by shared-memory bandwidth.  See profiles/r01c_notes.md.
+// Producer.  The kernel launches 384 threads: a third warpgroup drops to 24 registers (setmaxnreg) and its first
+// thread only waits for released stages and issues the TMA boxes, so the ring is always full and the two compute
+// groups (240 registers each) never wait for one another through it.
+//
+// Status: the default for this dilation set (CL4_SWEEP=nolattice selects the 4-pixel kernel).  B16 C21 512^2:
+// 0.516 ms per sweep against 0.613 ms; 72.9 M shared-memory wavefronts per launch against 98.5 M (ncu).  Nothing is
+// saturated (issue 48 %, l1tex 59 %, DRAM 48 %): with 8 compute warps per SM -- all that 48 register-resident weights per
+// pixel allow -- the loop is bound by instruction latency.  See profiles/r01c_notes.md and r01d_notes.md.
 //
 //   tile    32 x 32 pixels, 256 threads; window 80 rows x 84 columns per (tile, class), one
 //           cp.async.bulk.tensor box into a ring of stages with full/empty mbarriers.  The pitch of
