@@ -15,6 +15,15 @@ for (B, C, H, W, dil, T) in [(2, 5, 32, 32, [1, 2, 4, 8, 12], 3), (1, 3, 56, 56,
                              (1, 3, 96, 80, [1, 2, 4, 8, 12, 24], 2), (1, 2, 40, 40, [1, 2, 3, 4, 5, 6, 7, 8], 2)]:
     y = cl4.PAMR(T, dil).cuda()(torch.rand(B, 3, H, W, device=dev), torch.rand(B, C, H, W, device=dev).softmax(1))
     assert torch.isfinite(y).all()
+# the 4-pixel sweep (with its producer warpgroup) on the default dilation set, and the trainer's set on a large map
+os.environ["CL4_SWEEP"] = "nolattice"
+cl4.PAMR(2, [1, 2, 4, 8, 12, 24]).cuda()(torch.rand(1, 3, 96, 80, device=dev), torch.rand(1, 3, 96, 80, device=dev).softmax(1))
+del os.environ["CL4_SWEEP"]
+cl4.PAMR(2, [1, 2, 4, 8, 12]).cuda()(torch.rand(1, 3, 72, 100, device=dev), torch.rand(1, 2, 72, 100, device=dev).softmax(1))
+# phase-1 producers / consumers
+from cl4wsis_b200.wss import single_stage as ss
+ss.phase1_pseudo_labels(torch.randn(2, 3, 64, 80, device=dev), torch.randn(2, 5, 16, 20, device=dev), torch.ones(2, 4, device=dev),
+                        cl4.PAMR(3, [1, 2, 4, 8, 12]).cuda())
 x = torch.rand(1, 2, 20, 33, device=dev)
 for cls in (wm.LocalAffinity, wm.LocalAffinityAbs, wm.LocalAffinityCopy, wm.LocalStDev):
     cls([1, 2, 24]).cuda()(x)
