@@ -350,6 +350,29 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
         rc = dispatch_D<WeightsLauncher>(D, img, wts, B, K, H, W, dil, use_tma ? 1 : 0, s);
     }
     if (rc != CL4_OK) return rc;
+    if (use_lattice) {
+        // ping-pong in -> A -> B -> A ... -> out with no padding pass.  The scratch planes keep the (W + 48)-float row pitch
+        // of the padded layout (a power-of-two pitch such as 2048 bytes makes the 80 rows of a window collide in the memory
+        // system: 0.79 ms per sweep instead of 0.5 at 512 x 512); only their H x W image area is ever touched.
+        if ((rc = record(ev_sweeps_begin)) != CL4_OK) return rc;
+        const int sp = W + 2 * kPamrPad;
+        const long long splane = (long long)padded_plane_elems(H, W);
+        const float* cur = mask_in;
+        int cur_pitch = W;
+        long long cur_plane = (long long)H * W;
+        float* nxt = bufA;
+        for (int it = 0; it < num_iter; ++it) {
+            const bool last = (it == num_iter - 1);
+            float* dst = last ? mask_out : nxt;
+            rc = launch_sweep_lattice(wts, cur, cur_pitch, cur_plane, dst, last ? W : sp, last ? (long long)H * W : splane, B, C, H, W, s);
+            if (rc != CL4_OK) return rc;
+            cur = dst;
+            cur_pitch = sp;
+            cur_plane = splane;
+            nxt = (dst == bufA) ? bufB : bufA;
+        }
+        return record(ev_sweeps_end);
+    }
     if (use_tma) {
         // replicate-padded ping-pong: in -> A -> B -> A ... -> out (plain layout)
         const long long planes = (long long)B * C;
@@ -360,8 +383,7 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
         float* nxt = bufB;
         for (int it = 0; it < num_iter; ++it) {
             const bool last = (it == num_iter - 1);
-            rc = use_lattice ? launch_sweep_lattice(wts, cur, last ? mask_out : nxt, last ? 0 : 1, B, C, H, W, s)
-                             : launch_sweep_tma(wts, cur, last ? mask_out : nxt, last ? 0 : 1, B, C, H, W, dil, D, s);
+            rc = launch_sweep_tma(wts, cur, last ? mask_out : nxt, last ? 0 : 1, B, C, H, W, dil, D, s);
             if (rc != CL4_OK) return rc;
             if (!last) {
                 rc = launch_pad_frame(nxt, planes, H, W, s);

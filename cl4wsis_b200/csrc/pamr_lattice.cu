@@ -64,7 +64,7 @@ constexpr int kLWeightsPerTile = kLW * kLThreads;    // 49152 floats = 48 taps x
 #endif
 constexpr int kLFin = CL4_LATTICE_FINISHER;          // the group that adds the other's partial sums and stores (0: A, 1: B)
 constexpr int kLParts = CL4_LATTICE_PARTS;           // partial-sum buffers: how far group A may run ahead of group B
-constexpr size_t kLSmem = (size_t)kLStages * kLStageBytes + kLParts * kLPartFloats * 4 + (2 * kLStages + 8 * kLParts) * 8 + 64;
+constexpr size_t kLSmem = (size_t)kLStages * kLStageBytes + kLParts * kLPartFloats * 4 + (3 * kLStages + 8 * kLParts) * 8 + 64;
 
 // ---- who owns pixel (y, x) of a tile in each group: thread (0..127 within the group) and slot (0..7) ----
 struct Owner {
@@ -188,7 +188,7 @@ struct LatticeOut {
 struct LatticeCtx {
     float* stage0;
     float* part;  // [kLParts buffers][kLPartFloats]; pfull / pempty: [kLParts][4 warp pairs]
-    uint64_t *full, *empty, *pfull, *pempty;
+    uint64_t *full, *ready, *empty, *pfull, *pempty;  // full: TMA landed; ready: border patched (what the compute warps wait for)
     const float* wts;
     int C, H, W, tiles_x, tiles_per_img, n_my, total, s0;
 };
@@ -221,7 +221,70 @@ __device__ __forceinline__ void lattice_producer(const LatticeCtx& cx, const CUt
         if (pk == cx.n_my) pk = 0;
         const LTile ptc = ltile(blockIdx.x + pk * gridDim.x, cx.tiles_x, cx.tiles_per_img);
         mbar_arrive_expect_tx(&cx.full[s], kLStageBytes);
-        tma_load_3d(cx.stage0 + (size_t)s * kLStageFloats, tmap, &cx.full[s], ptc.x0, ptc.y0, ptc.b * C + pc);
+        tma_load_3d(cx.stage0 + (size_t)s * kLStageFloats, tmap, &cx.full[s], ptc.x0 - kHalo, ptc.y0 - kHalo, ptc.b * C + pc);
+    }
+}
+
+// Replicate padding inside the ring (reference wss/modules.py:57: F.pad(mode="replicate")).  The planes in HBM are
+// NOT padded: the TMA box starts 24 pixels up-left of the tile and the hardware zero-fills what lies outside the plane.
+// The three otherwise idle warps of the producer warpgroup turn those zeros into the clamped neighbour before the
+// compute warps see the window: every cell outside the image takes the value of the nearest image pixel, which lies
+// inside the same window.  Interior tiles need nothing.  This replaces the replicate-padded planes in HBM, the copy
+// into them and the frame rewrite after every sweep (10 % of the step before).
+__device__ __forceinline__ void lattice_patcher(const LatticeCtx& cx) {
+    const int C = cx.C;
+    const int lane = threadIdx.x & 31, pw = (threadIdx.x >> 5) - (kLThreads / 32 + 1);  // patch warp 0..2
+    for (int item = 0; item < cx.total; ++item) {
+        const int s = item % kLStages;
+        const int v = item + cx.s0;
+        int pk = v / C;
+        if (pk == cx.n_my) pk = 0;
+        const LTile tc = ltile(blockIdx.x + pk * gridDim.x, cx.tiles_x, cx.tiles_per_img);
+        // valid window rows [rv0, rv1) and columns [cv0, cv1): the part of the 80 x 84 window that lies inside the image
+        const int rv0 = max(0, kHalo - tc.y0), rv1 = min(kBox, cx.H - tc.y0 + kHalo);
+        const int cv0 = max(0, kHalo - tc.x0), cv1 = min(kLPitch, cx.W - tc.x0 + kHalo);
+        mbar_wait_relaxed(&cx.full[s], (uint32_t)((item / kLStages) & 1));  // suspended, not spinning
+#ifdef CL4_EXP_PATCH_NOWORK  // experiment: the ready handshake without the patching
+        if (false) {
+#else
+        if (rv0 > 0 || rv1 < kBox || cv0 > 0 || cv1 < kLPitch) {
+#endif
+            float* win = cx.stage0 + (size_t)s * kLStageFloats;
+            const int t = pw * 32 + lane;  // 0..95
+            // columns left / right of the image: one thread per valid window row, independent stores of one value
+            const int r = rv0 + t;
+            if (r < rv1) {
+                float* row = win + r * kLPitch;
+                if (cv0 > 0) {
+                    const float v = row[cv0];
+#pragma unroll 8
+                    for (int c = 0; c < cv0; ++c) row[c] = v;
+                }
+                if (cv1 < kLPitch) {
+                    const float v = row[cv1 - 1];
+#pragma unroll 4
+                    for (int c = cv1; c < kLPitch; ++c) row[c] = v;
+                }
+            }
+            // rows above / below the image: one thread per window column; the source is the clamped column of the first /
+            // last image row, a cell the loop above does not write
+            if (t < kLPitch) {
+                const int cs = min(max(t, cv0), cv1 - 1);
+                if (rv0 > 0) {
+                    const float v = win[rv0 * kLPitch + cs];
+#pragma unroll 8
+                    for (int q = 0; q < rv0; ++q) win[q * kLPitch + t] = v;
+                }
+                if (rv1 < kBox) {
+                    const float v = win[(rv1 - 1) * kLPitch + cs];
+#pragma unroll 4
+                    for (int q = rv1; q < kBox; ++q) win[q * kLPitch + t] = v;
+                }
+            }
+            fence_proxy_async_smem();  // these generic-proxy writes are ordered before the next TMA refill of the stage
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cx.ready[s]);
     }
 }
 
@@ -289,7 +352,11 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
 
     // loop state kept incrementally (no division per item): ring stage + phase, partial buffer + phase,
     // window pointer, hand-over barrier of this warp pair
+#ifdef CL4_EXP_NOPATCH  // experiment: no border patching, consumers wait for the TMA directly (wrong borders)
     const uint32_t full0 = smem_u32(cx.full), empty0 = smem_u32(cx.empty);
+#else
+    const uint32_t full0 = smem_u32(cx.ready), empty0 = smem_u32(cx.empty);  // "full" for the compute warps = patched
+#endif
     const uint32_t pfull0 = smem_u32(cx.pfull) + 8u * ((tid >> 5) & 3), pempty0 = smem_u32(cx.pempty) + 8u * ((tid >> 5) & 3);
     int stage = 0, pb = 0;
     uint32_t full_phase = 0, part_phase = 0;
@@ -399,7 +466,8 @@ pamr_sweep_lattice_kernel(const __grid_constant__ CUtensorMap tmap, const float*
     cx.stage0 = reinterpret_cast<float*>(smem_raw);
     cx.part = cx.stage0 + (size_t)kLStages * kLStageFloats;
     cx.full = reinterpret_cast<uint64_t*>(cx.part + kLParts * kLPartFloats);
-    cx.empty = cx.full + kLStages;
+    cx.ready = cx.full + kLStages;
+    cx.empty = cx.ready + kLStages;
     cx.pfull = cx.empty + kLStages;
     cx.pempty = cx.pfull + 4 * kLParts;
     cx.wts = wts;
@@ -416,6 +484,7 @@ pamr_sweep_lattice_kernel(const __grid_constant__ CUtensorMap tmap, const float*
         tma_prefetch_desc(&tmap);
         for (int s = 0; s < kLStages; ++s) {
             mbar_init(&cx.full[s], 1);
+            mbar_init(&cx.ready[s], 3);               // the three patch warps
             mbar_init(&cx.empty[s], kLThreads / 32);  // the eight compute warps
         }
         for (int s = 0; s < 4 * kLParts; ++s) {
@@ -427,9 +496,14 @@ pamr_sweep_lattice_kernel(const __grid_constant__ CUtensorMap tmap, const float*
     __syncthreads();
 
     if (threadIdx.x >= kLThreads) {  // producer warpgroup: hand its registers to the compute warps
+        // the CTA owns 384 x 168 registers; what this warpgroup gives back ((168 - 24) x 128) is exactly what the two
+        // compute warpgroups take ((240 - 168) x 256) -- a larger value here would leave their setmaxnreg.inc waiting forever
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
 #ifndef CL4_LATTICE_NOTMA  // ablation: compute on whatever the stages hold
         if (threadIdx.x == kLThreads) lattice_producer(cx, &tmap);
+#ifndef CL4_EXP_NOPATCH
+        else if (threadIdx.x >= kLThreads + 32) lattice_patcher(cx);
+#endif
 #endif
         return;
     }
@@ -566,25 +640,18 @@ int launch_weights_lattice(const float* padded_img, float* w, int B, int K, int 
     return check_launch("pamr_weights_lattice");
 }
 
-int launch_sweep_lattice(const float* w, const float* padded_in, float* out, int out_padded, int B, int C, int H, int W,
-                         cudaStream_t s) {
-    CUtensorMap tmap;
-    const int Wp = W + 2 * kHalo, Hp = H + 2 * kHalo;
-    const int rc = encode_tmap_3d_f32(&tmap, padded_in, Wp, Hp, (long long)B * C, kLPitch, kBox);
+int launch_sweep_lattice(const float* w, const float* in, int in_pitch, long long in_plane, float* out, int out_pitch,
+                         long long out_plane, int B, int C, int H, int W, cudaStream_t s) {
+    CUtensorMap tmap;  // over the H x W image area of each plane; boxes may start at negative coordinates (zero fill)
+    const int rc = encode_tmap_3d_f32_strided(&tmap, in, W, H, (long long)B * C, in_pitch, in_plane, kLPitch, kBox);
     if (rc != 0) {
         set_error("pamr_sweep_lattice: cuTensorMapEncodeTiled failed (%d)", rc);
         return CL4_ECUDA;
     }
     LatticeOut so;
-    if (out_padded) {
-        so.ptr = out + (size_t)kHalo * Wp + kHalo;
-        so.plane = (long long)Hp * Wp;
-        so.pitch = Wp;
-    } else {
-        so.ptr = out;
-        so.plane = (long long)H * W;
-        so.pitch = W;
-    }
+    so.ptr = out;
+    so.plane = out_plane;
+    so.pitch = out_pitch;
     const int tiles_x = ceil_div(W, kTile), tiles_y = ceil_div(H, kTile);
     const int n_tiles = B * tiles_x * tiles_y;
     cudaError_t e = cudaFuncSetAttribute(pamr_sweep_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmem);

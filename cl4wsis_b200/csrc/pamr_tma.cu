@@ -450,10 +450,15 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tmap_3d_f32(CUtensorMap* map, const float* base, int W, int H, long long planes, int bx, int by) {
+    return encode_tmap_3d_f32_strided(map, base, W, H, planes, W, (long long)W * H, bx, by);
+}
+
+int encode_tmap_3d_f32_strided(CUtensorMap* map, const float* base, int W, int H, long long planes, int pitch,
+                               long long plane_elems, int bx, int by) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return -1;
     cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
-    cuuint64_t gstride[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+    cuuint64_t gstride[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)plane_elems * 4};
     cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,

@@ -111,5 +111,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // Host: encode a rank-3 fp32 tensor map over [planes][H][W] with box (bx, by, 1).
 // Returns 0 on success, a CUresult (>0) or -1 when the driver entry point is unavailable.
 int encode_tmap_3d_f32(CUtensorMap* map, const float* base, int W, int H, long long planes, int bx, int by);
+// the same over a sub-window of a larger allocation: rows `pitch` and planes `plane_elems` elements apart; elements
+// outside [0,W) x [0,H) are zero-filled even where memory exists
+int encode_tmap_3d_f32_strided(CUtensorMap* map, const float* base, int W, int H, long long planes, int pitch,
+                               long long plane_elems, int bx, int by);
 
 }  // namespace cl4

@@ -36,8 +36,13 @@ class PseudoLabelStep:
         self.ids = torch.empty((B, H, W), dtype=torch.int64, device=dev)
         self.centers = torch.zeros((B, self.max_centers, 2), dtype=torch.int64, device=dev)
         self.counts = torch.zeros((B,), dtype=torch.int32, device=dev)
-        # launches per step: image pad, weights, mask pad, num_iter sweeps, num_iter-1 frame rewrites, 2 NMS, grouping
-        self.launches_per_step = 1 + 1 + 1 + self.num_iter + max(self.num_iter - 1, 0) + 2 + 1
+        # launches per step.  Lattice sweep (class-default dilations, the replicate padding happens inside the kernel):
+        # image pad, weights, num_iter sweeps, 2 NMS, grouping.  4-pixel TMA sweep: + mask pad and num_iter-1 frame rewrites.
+        import os
+        lattice = (self.dil == [1, 2, 4, 8, 12, 24] and K <= 3 and W % 4 == 0 and H * W > 64 * 64
+                   and os.environ.get("CL4_SWEEP") in (None, "", "lattice"))
+        self.launches_per_step = (1 + 1 + self.num_iter + 2 + 1 if lattice
+                                  else 1 + 1 + 1 + self.num_iter + max(self.num_iter - 1, 0) + 2 + 1)
 
     def run(self, img, mask, heat, offsets, fg=None, stream=None, sweep_events=None):
         """All arguments are contiguous fp32 CUDA tensors: img [B,K,H,W], mask [B,C,H,W],
