@@ -21,8 +21,12 @@
 // thread only waits for released stages and issues the TMA boxes, so the ring is always full and the two compute
 // groups (240 registers each) never wait for one another through it.
 //
+// Padding.  The planes in HBM are not padded: a window's box starts 24 pixels up-left of its tile, the TMA unit zero-fills
+// what lies outside the plane, and the other three warps of the producer warpgroup write the clamped neighbour
+// (wss/modules.py:57, replicate padding) into those cells before the compute warps see the window.
+//
 // Status: the default for this dilation set (CL4_SWEEP=nolattice selects the 4-pixel kernel).  B16 C21 512^2:
-// 0.516 ms per sweep against 0.613 ms; 72.9 M shared-memory wavefronts per launch against 98.5 M (ncu).  Nothing is
+// 0.506 ms per sweep and no padding / frame kernels against 0.613 + 0.025 ms; 72.9 M shared-memory wavefronts per launch against 98.5 M (ncu).  Nothing is
 // saturated (issue 48 %, l1tex 59 %, DRAM 48 %): with 8 compute warps per SM -- all that 48 register-resident weights per
 // pixel allow -- the loop is bound by instruction latency.  See profiles/r01c_notes.md and r01d_notes.md.
 //
@@ -40,7 +44,7 @@
 namespace cl4 {
 
 #ifndef CL4_LATTICE_STAGES
-#define CL4_LATTICE_STAGES 5
+#define CL4_LATTICE_STAGES 4  // 3..6 measure within 3 %; 4 stages + 2 partial buffers is the fastest (0.506 ms)
 #endif
 
 constexpr int kLThreads = 256;                       // 8 compute warps: 0-3 group A, 4-7 group B
@@ -57,7 +61,7 @@ constexpr int kLTaps = 24;                           // taps per thread and pixe
 constexpr int kLW = kLPx * kLTaps;                   // 192 weight registers
 constexpr int kLWeightsPerTile = kLW * kLThreads;    // 49152 floats = 48 taps x 1024 pixels
 #ifndef CL4_LATTICE_PARTS
-#define CL4_LATTICE_PARTS 4
+#define CL4_LATTICE_PARTS 2
 #endif
 #ifndef CL4_LATTICE_FINISHER
 #define CL4_LATTICE_FINISHER 1
