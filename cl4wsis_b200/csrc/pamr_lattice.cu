@@ -238,16 +238,22 @@ __device__ __forceinline__ void lattice_producer(const LatticeCtx& cx, const CUt
 __device__ __forceinline__ void lattice_patcher(const LatticeCtx& cx) {
     const int C = cx.C;
     const int lane = threadIdx.x & 31, pw = (threadIdx.x >> 5) - (kLThreads / 32 + 1);  // patch warp 0..2
-    for (int item = 0; item < cx.total; ++item) {
-        const int s = item % kLStages;
-        const int v = item + cx.s0;
-        int pk = v / C;
-        if (pk == cx.n_my) pk = 0;
-        const LTile tc = ltile(blockIdx.x + pk * gridDim.x, cx.tiles_x, cx.tiles_per_img);
+    // per-tile geometry is recomputed only when the tile changes (no division on the per-item path: the time between
+    // `full` and `ready` is on the critical path of the ring)
+    int k = 0, c = cx.s0, s = 0;
+    uint32_t phase = 0;
+    int rv0 = 0, rv1 = kBox, cv0 = 0, cv1 = kLPitch;
+    auto enter_tile = [&](int kk) {
+        const LTile tc = ltile(blockIdx.x + kk * gridDim.x, cx.tiles_x, cx.tiles_per_img);
         // valid window rows [rv0, rv1) and columns [cv0, cv1): the part of the 80 x 84 window that lies inside the image
-        const int rv0 = max(0, kHalo - tc.y0), rv1 = min(kBox, cx.H - tc.y0 + kHalo);
-        const int cv0 = max(0, kHalo - tc.x0), cv1 = min(kLPitch, cx.W - tc.x0 + kHalo);
-        mbar_wait_relaxed(&cx.full[s], (uint32_t)((item / kLStages) & 1));  // suspended, not spinning
+        rv0 = max(0, kHalo - tc.y0);
+        rv1 = min(kBox, cx.H - tc.y0 + kHalo);
+        cv0 = max(0, kHalo - tc.x0);
+        cv1 = min(kLPitch, cx.W - tc.x0 + kHalo);
+    };
+    if (cx.total > 0) enter_tile(0);
+    for (int item = 0; item < cx.total; ++item) {
+        mbar_wait_relaxed(&cx.full[s], phase);  // suspended, not spinning
 #ifdef CL4_EXP_PATCH_NOWORK  // experiment: the ready handshake without the patching
         if (false) {
 #else
@@ -289,6 +295,18 @@ __device__ __forceinline__ void lattice_patcher(const LatticeCtx& cx) {
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&cx.ready[s]);
+        if (++s == kLStages) {
+            s = 0;
+            phase ^= 1u;
+        }
+        if (++c == C) {
+            c = 0;
+            const int nk = (k + 1 == cx.n_my) ? 0 : k + 1;
+            if (nk != k) {
+                k = nk;
+                enter_tile(k);
+            }
+        }
     }
 }
 
