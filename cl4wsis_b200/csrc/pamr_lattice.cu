@@ -216,16 +216,27 @@ __device__ __forceinline__ LTile ltile(int t, int tiles_x, int tiles_per_img) {
 // leading group collapses and random CTAs ran whole launches 1.75x slower -- profiles/r01c_notes.md.)
 __device__ __forceinline__ void lattice_producer(const LatticeCtx& cx, const CUtensorMap* tmap) {
     const int C = cx.C;
+    // the coordinates of the next box are ready before the wait (tile geometry only changes every C items), so the TMA
+    // goes out the moment the stage is released: the release -> refill latency is on the critical path of the ring
+    int k = 0, c = cx.s0, s = 0;
+    uint32_t phase = 1;  // parity of the previous use of the stage
+    LTile tc = ltile(blockIdx.x, cx.tiles_x, cx.tiles_per_img);
     for (int p_item = 0; p_item < cx.total; ++p_item) {
-        const int s = p_item % kLStages;
-        if (p_item >= kLStages) mbar_wait_relaxed(&cx.empty[s], (uint32_t)((p_item / kLStages - 1) & 1));
-        const int v = p_item + cx.s0;
-        int pk = v / C;
-        const int pc = v - pk * C;
-        if (pk == cx.n_my) pk = 0;
-        const LTile ptc = ltile(blockIdx.x + pk * gridDim.x, cx.tiles_x, cx.tiles_per_img);
+        if (p_item >= kLStages) mbar_wait_relaxed(&cx.empty[s], phase);
         mbar_arrive_expect_tx(&cx.full[s], kLStageBytes);
-        tma_load_3d(cx.stage0 + (size_t)s * kLStageFloats, tmap, &cx.full[s], ptc.x0 - kHalo, ptc.y0 - kHalo, ptc.b * C + pc);
+        tma_load_3d(cx.stage0 + (size_t)s * kLStageFloats, tmap, &cx.full[s], tc.x0 - kHalo, tc.y0 - kHalo, tc.b * C + c);
+        if (++s == kLStages) {
+            s = 0;
+            phase ^= 1u;
+        }
+        if (++c == C) {
+            c = 0;
+            const int nk = (k + 1 == cx.n_my) ? 0 : k + 1;
+            if (nk != k) {
+                k = nk;
+                tc = ltile(blockIdx.x + k * gridDim.x, cx.tiles_x, cx.tiles_per_img);
+            }
+        }
     }
 }
 
