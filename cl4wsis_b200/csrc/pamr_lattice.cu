@@ -63,10 +63,14 @@ constexpr int kLWeightsPerTile = kLW * kLThreads;    // 49152 floats = 48 taps x
 #ifndef CL4_LATTICE_PARTS
 #define CL4_LATTICE_PARTS 2
 #endif
+#ifndef CL4_LATTICE_APAIR
+#define CL4_LATTICE_APAIR 0
+#endif
 #ifndef CL4_LATTICE_FINISHER
 #define CL4_LATTICE_FINISHER 1
 #endif
 constexpr int kLFin = CL4_LATTICE_FINISHER;          // the group that adds the other's partial sums and stores (0: A, 1: B)
+static_assert(!CL4_LATTICE_APAIR || CL4_LATTICE_FINISHER == 1, "the pair variant of group A only hands over");
 constexpr int kLParts = CL4_LATTICE_PARTS;           // partial-sum buffers: how far group A may run ahead of group B
 constexpr size_t kLSmem = (size_t)kLStages * kLStageBytes + kLParts * kLPartFloats * 4 + (3 * kLStages + 8 * kLParts) * 8 + 64;
 
@@ -74,11 +78,24 @@ constexpr size_t kLSmem = (size_t)kLStages * kLStageBytes + kLParts * kLPartFloa
 struct Owner {
     int thread, slot;
 };
+constexpr bool kLAPair = CL4_LATTICE_APAIR != 0;  // group A on pairs of adjacent columns (LDS.64) instead of single lattice columns
+#if CL4_LATTICE_APAIR
+// group A, pair variant: a thread owns rows y0, y0+4 x column pairs (x0, x0+1), (x0+4, x0+5), x0 in {0, 2}: a 2 x 2
+// lattice block of float2.  8 x 8 super-blocks of 8 threads; a warp = the four super-blocks of one 8-row band, its
+// half-warps take super-blocks {0, 2} / {1, 3} so that the 16 float2 of an LDS.64 fall into 16 different bank pairs
+// (window pitch 84, partial pitch 36).  slot = ((i*2 + j)*2 + e).
+__host__ __device__ inline Owner owner_a(int y, int x) {
+    const int sby = y >> 3, ry = y & 7, sbx = x >> 3, rx = x & 7;
+    const int lane = (sbx & 1) * 16 + (sbx >> 1) * 8 + (ry & 3) * 2 + ((rx & 3) >> 1);
+    return Owner{sby * 32 + lane, (((ry >> 2) * 2 + (rx >> 2)) * 2) + (rx & 1)};
+}
+#else
 // group A: 2 x 4 lattice blocks of spacing 4 inside 8 x 16 super-blocks (16 threads = 4 x 4 phases)
 __host__ __device__ inline Owner owner_a(int y, int x) {
     const int sby = y >> 3, ry = y & 7, sbx = x >> 4, rx = x & 15;
     return Owner{(sby * 2 + sbx) * 16 + (ry & 3) * 4 + (rx & 3), (ry >> 2) * 4 + (rx >> 2)};
 }
+#endif
 // group B: 4 x 2 blocks of adjacent pixels, 16 blocks per row of blocks (one half-warp)
 __host__ __device__ inline Owner owner_b(int y, int x) { return Owner{(y >> 2) * 16 + (x >> 1), (y & 3) * 2 + (x & 1)}; }
 
@@ -148,6 +165,37 @@ __device__ __forceinline__ void group_a_class(float (&w)[kLW], float (&acc)[kLPx
             if (source_needed<2, 4, 3>(r, c)) {
                 const float v = sp[r * 4 * kLPitch + c * 4];
                 feed<2, 4, 3, kReload>(w, acc, v, r, c, nw);
+            }
+}
+
+// group A, pair variant: a 2 x 2 lattice block of column pairs; every lattice position is one float2 whose halves feed
+// the two pixels of a pair.  56 of the 8 x 8 lattice positions are read (56 LDS.64 for 192 FMAs).
+template <bool kReload>
+__device__ __forceinline__ void group_a_pair_class(float (&w)[kLW], float (&acc)[kLPx], const float* __restrict__ sp,
+                                                   const float4* __restrict__ nw) {
+#pragma unroll
+    for (int r = -3; r < 2 + 3; ++r)
+#pragma unroll
+        for (int c = -3; c < 2 + 3; ++c)
+            if (source_needed<2, 2, 3>(r, c)) {
+                const float2 v = *reinterpret_cast<const float2*>(sp + r * 4 * kLPitch + c * 4);
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int st = 1; st <= 3; ++st) {
+                            const int di = r - i, dj = c - j;
+                            if (is_tap(di, dj, st)) {
+                                const int k = ((i * 2 + j) * 2) * kLTaps + (st - 1) * 8 + tap_index(di / st, dj / st);
+                                acc[(i * 2 + j) * 2] = fmaf(w[k], v.x, acc[(i * 2 + j) * 2]);
+                                acc[(i * 2 + j) * 2 + 1] = fmaf(w[k + kLTaps], v.y, acc[(i * 2 + j) * 2 + 1]);
+                                if (kReload && (k & 3) == 3) {
+                                    load_weight_group(w, nw, k >> 2);
+                                    load_weight_group(w, nw, (k + kLTaps) >> 2);
+                                }
+                            }
+                        }
             }
 }
 
@@ -331,7 +379,11 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
 
     // thread geometry: tile-relative row / column of the thread's block origin
     int ry, rx;
-    if (G == 0) {
+    if (G == 0 && kLAPair) {
+        const int ln = tg & 31, sbx = ((ln >> 3) & 1) * 2 + (ln >> 4);
+        ry = (tg >> 5) * 8 + ((ln >> 1) & 3);
+        rx = sbx * 8 + (ln & 1) * 2;
+    } else if (G == 0) {
         const int sb = tg >> 4;
         ry = (sb >> 1) * 8 + ((tg >> 2) & 3);
         rx = (sb & 1) * 16 + (tg & 3);
@@ -413,7 +465,10 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
 
 #pragma unroll
         for (int i = 0; i < kLPx; ++i) acc[i] = 0.f;
-        if (G == 0) {
+        if (G == 0 && kLAPair) {
+            if (reload) group_a_pair_class<true>(w, acc, sp, nw);
+            else group_a_pair_class<false>(w, acc, sp, nw);
+        } else if (G == 0) {
             if (reload) group_a_class<true>(w, acc, sp, nw);
             else group_a_class<false>(w, acc, sp, nw);
         } else {
@@ -428,7 +483,14 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
 #ifndef CL4_LATTICE_NOHANDOVER  // ablation: free-running groups (wrong results)
             if (item >= kLParts) mbar_wait_u32(pempty0 + 32u * pb, part_phase ^ 1u);
 #endif
-            if (G == 0) {
+            if (G == 0 && kLAPair) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        *reinterpret_cast<float2*>(pp + i * 4 * kLPartPitch + j * 4) =
+                            make_float2(acc[(i * 2 + j) * 2], acc[(i * 2 + j) * 2 + 1]);
+            } else if (G == 0) {
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
 #pragma unroll
