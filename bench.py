@@ -369,9 +369,9 @@ def main():
         smem_bytes = float("nan")
     sm_hz = (clk.get("sm_mhz") or 1965) * 1e6
     # dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch from the committed ncu --set full
-    # capture of this workload (profiles/r01e_sweep_ncu_raw.csv: 1.677 GB read + 0.343 GB written by the lattice sweep;
+    # capture of this workload (profiles/r01f_sweep_ncu_raw.csv: 1.557 GB read + 0.342 GB written by the lattice sweep;
     # profiles/r01b_sweep_ncu_raw.csv: 1.892 GB for the 4-pixel sweep); other workloads were not captured
-    traffic = (2.020e9 if lattice else 1.892e9) if args.workload == "voc_b16_c21_512" else None
+    traffic = (1.900e9 if lattice else 1.892e9) if args.workload == "voc_b16_c21_512" else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
         "ms_per_step": 1e3 * stats["elapsed_s"] / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
