@@ -26,6 +26,27 @@ import sys
 import threading
 import time
 
+# stdout carries exactly one JSON line.  NCCL writes its version banner (and NCCL_DEBUG output) straight to file descriptor 1,
+# so descriptor 1 points at stderr while the benchmark runs and is restored for the final line (_emit).
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_STDOUT_FD = None
+
+
+def _divert_stdout():
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+
+
 import numpy as np
 import torch
 
@@ -191,7 +212,7 @@ def run_reference_arm(args, cfg, rank, world):
         "note": "reference is pure Python/PyTorch and cannot travel to the GPU box; this is oracle/cl4_oracle.c "
                 "(C + OpenMP port, ~12x faster than the reference's own torch-CPU path measured in SURVEY §6)",
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------- widened rows
@@ -264,6 +285,7 @@ def main():
     ap.add_argument("--no-callers", action="store_true", help="skip the timing of the widened rows (refine / pseudo labels)")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
+    _divert_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -398,7 +420,7 @@ def main():
         line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{args.cpu_images} images of workload {args.workload}, oracle/cl4_oracle.c "
                                           f"(C+OpenMP), {dt:.1f} s"}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 if __name__ == "__main__":

@@ -10,6 +10,7 @@ import json
 import os
 import sys
 
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the JSON line
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
