@@ -1,24 +1,25 @@
-// PAMR propagation sweep, TMA-staged (reference wss/modules.py:148-149).
+// PAMR propagation sweep, TMA-staged, four pixels x all taps per thread (reference wss/modules.py:148-149).
+// The path of every dilation set other than the class default (which takes pamr_lattice.cu), D <= 6, dilations <= 24.
 //
 // Layout.  Between sweeps the masks live in HBM as REPLICATE-PADDED planes
 // [B*C][H+48][W+48] (24 = largest dilation): the clamped neighbour of wss/modules.py:57 is then
 // an ordinary in-bounds read, every 80x80 source window is a plain TMA box and the hot loop has
 // no border case.  A small kernel rewrites the 24-pixel frame after each sweep.
 //
-// Sweep kernel.  One persistent CTA per SM (256 threads) walks over 32x32-pixel output tiles in
-// image-major order (neighbouring CTAs share halos in L2).  A thread owns four pixels of one
-// column, 4 rows apart, and keeps their 4 x 8D affinity weights in registers for all C classes
-// of the tile (the weights are the only per-pixel state; 192 registers at D = 6).  Per class the
-// 80x80 window arrives by ONE cp.async.bulk.tensor box load into a 4-stage shared-memory ring
-// guarded by full/empty mbarriers, so the copies of the next three classes overlap the FMAs
-// (3 to 6 stages measure the same; 8 is slower because the L1 left for the weight refill shrinks).
-// The inner loop is LDS (immediate offset) + FFMA; because the four pixels sit 4 rows apart,
-// 39 of their 192 (pixel, tap) sources coincide and are loaded once (153 LDS per 192 FFMA) —
-// the loop is bound by shared-memory bandwidth (one 128-byte wavefront per cycle), not by FP32.
-// While the last class of a tile is computed, each weight register is refilled with the next
-// tile's value right after its final use, which hides the 196 KB weight fetch.  The weights are
-// stored tile-major ([tile][p/4][32][32][4], written by the weights kernel): a thread's 192 weights
-// are 48 float4 loads at immediate offsets from one pointer.
+// Sweep kernel.  One persistent CTA per SM walks over 32x32-pixel output tiles in image-major order
+// (neighbouring CTAs share halos in L2).  A thread owns four pixels of one column, 4 rows apart, and
+// keeps their 4 x 8D affinity weights in registers for all C classes of the tile (the weights are the
+// only per-pixel state; 192 registers at D = 6).  Per class the 80x80 window arrives by ONE
+// cp.async.bulk.tensor box load into a 4-stage shared-memory ring guarded by full/empty mbarriers
+// (3 to 6 stages and 2 to 5 windows ahead measure the same).  The inner loop is LDS (immediate
+// offset) + FFMA; because the four pixels sit 4 rows apart, 49 of their 192 (pixel, tap) sources
+// coincide and are loaded once (143 LDS per 192 FFMA at D = 6).  It is bound by instruction latency at
+// 8 warps per SM, not by a bandwidth (profiles/r01c_notes.md, r01d_notes.md).
+// While the last class of a tile is computed the weight registers are refilled with the next tile's
+// values; the weights are stored tile-major ([tile][p/4][32][32][4], written by the weights kernel): a
+// thread's 192 weights are 48 float4 loads at immediate offsets from one pointer.
+// kWS (D >= 4, default): 384 threads, the third warpgroup's first thread is the TMA producer and the compute
+// warps take its registers through setmaxnreg (see pamr_sweep_tma_kernel).
 #include <stdlib.h>
 #include <string.h>
 

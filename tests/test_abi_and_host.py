@@ -120,3 +120,22 @@ def test_opencv_8_connectivity_label_order_rule():
             info[perm[k - 1], 0] = np.flatnonzero((lab == k).ravel())[0]
         order = _opencv_label_order(comp, info, list(range(n - 1)))
         assert order == [int(perm[k - 1]) for k in range(1, n)]
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py contract: exactly one JSON line on stdout; the reference arm runs on the CPU (oracle port) with the
+    base contract's keys plus impl / cpu_baseline / e2e."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-images", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
