@@ -53,6 +53,7 @@ SIGNATURES = {
                                     ctypes.POINTER(_flt), _vp]),
     "cl4_softmax_channels": (_int, [_vp, _vp, _int, _int, ctypes.c_longlong, _vp]),
     "cl4_pseudo_gtmask": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _flt, _flt, _flt, _int, _vp]),
+    "cl4_lattice_owner": (_int, [_int, _int, _int, ctypes.POINTER(_int), ctypes.POINTER(_int)]),
     "cl4_group_pixels": (_int, [_vp, _vp, _int, _int, _vp, _vp, _vp, _int, _int, _int, _int, _vp]),
 }
 

@@ -761,3 +761,15 @@ int launch_sweep_lattice(const float* w, const float* in, int in_pitch, long lon
 
 }  // namespace cl4
 
+// Layout introspection (host only, no GPU needed): which thread of which warp group holds the weights of pixel (y, x) of a
+// 32 x 32 tile, and in which of its 8 pixel slots.  tests/test_abi_and_host.py checks the invariants the kernels rely on
+// (a bijection per group, warp pairs owning the same rows, bank-conflict-free lane patterns).
+extern "C" int cl4_lattice_owner(int group, int y, int x, int* thread_out, int* slot_out) {
+    CL4_REQUIRE(group >= 0 && group <= 1 && y >= 0 && y < cl4::kTile && x >= 0 && x < cl4::kTile && thread_out && slot_out,
+                CL4_EINVAL, "lattice_owner: group 0/1, pixel inside the 32 x 32 tile");
+    const cl4::Owner o = group == 0 ? cl4::owner_a(y, x) : cl4::owner_b(y, x);
+    *thread_out = o.thread;
+    *slot_out = o.slot;
+    return CL4_OK;
+}
+

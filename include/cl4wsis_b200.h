@@ -226,6 +226,12 @@ int cl4_pseudo_gtmask(const float* mask, const float* labels, float* gated_out, 
                       int B, int C, int HW, float cutoff_top, float cutoff_bkg, float cutoff_low, int ambiguous,
                       cl4_stream_t stream);
 
+/* Layout introspection of the default propagation kernel (host only): the thread (0..127 of warp group `group`, 0 = dilations
+ * {4,8,12}, 1 = {1,2,24}) and pixel slot (0..7) that hold the affinity weights of pixel (y, x) of a 32 x 32 tile; the weight
+ * of tap t (0..23 within the group) sits at float index ((slot*24 + t)/4 * 256 + group*128 + thread)*4 + t%4 of the tile's
+ * 49152-float block in the scratch buffer.  No reference counterpart (wss/modules.py keeps weights as a [B,1,8D,H,W] tensor). */
+int cl4_lattice_owner(int group, int y, int x, int* thread_out, int* slot_out);
+
 #ifdef __cplusplus
 }
 #endif

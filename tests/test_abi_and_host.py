@@ -139,3 +139,46 @@ def test_bench_reference_arm_prints_one_json_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_lattice_sweep_layout_invariants(lib):
+    """The (pixel -> thread, slot) maps of the default propagation kernel (pamr_lattice.cu), read through the C ABI:
+    a bijection per warp group; A's warp j and B's warp j own the same 8 tile rows (their partial sums meet per warp pair);
+    the lane patterns are bank-conflict free at the window pitch of 84 floats and the partial-sum pitch of 36."""
+    import ctypes
+    t, s = ctypes.c_int(), ctypes.c_int()
+    own = {}
+    for g in (0, 1):
+        seen = set()
+        for y in range(32):
+            for x in range(32):
+                assert lib.cl4_lattice_owner(g, y, x, ctypes.byref(t), ctypes.byref(s)) == 0
+                assert 0 <= t.value < 128 and 0 <= s.value < 8
+                seen.add((t.value, s.value))
+                own[g, y, x] = (t.value, s.value)
+        assert len(seen) == 1024
+    assert lib.cl4_lattice_owner(2, 0, 0, ctypes.byref(t), ctypes.byref(s)) != 0
+    assert lib.cl4_lattice_owner(0, 32, 0, ctypes.byref(t), ctypes.byref(s)) != 0
+    for g in (0, 1):  # warp j <-> rows 8j .. 8j+7
+        for (gg, y, x), (th, _) in own.items():
+            if gg == g:
+                assert th // 32 == y // 8
+    # block origin (slot 0) of every thread
+    origin = {(g, th): (y, x) for (g, y, x), (th, sl) in own.items() if sl == 0}
+    # group A: slots are a 2 x 4 lattice block of spacing 4
+    for (g, y, x), (th, sl) in own.items():
+        if g == 0:
+            oy, ox = origin[0, th]
+            assert (y - oy, x - ox) == (4 * (sl // 4), 4 * (sl % 4))
+        else:  # group B: 4 x 2 block of adjacent pixels
+            oy, ox = origin[1, th]
+            assert (y - oy, x - ox) == (sl // 2, sl % 2)
+    for pitch in (84, 36):
+        for w in range(4):
+            # A: 32-bit accesses, all 32 lanes of a warp in distinct banks
+            banks = {(origin[0, 32 * w + ln][0] * pitch + origin[0, 32 * w + ln][1]) % 32 for ln in range(32)}
+            assert len(banks) == 32, (pitch, w)
+            # B: 64-bit accesses, the 16 lanes of a half-warp in distinct bank pairs
+            for h in range(2):
+                pairs = {((origin[1, 32 * w + 16 * h + ln][0] * pitch + origin[1, 32 * w + 16 * h + ln][1]) // 2) % 16 for ln in range(16)}
+                assert len(pairs) == 16, (pitch, w, h)
