@@ -297,6 +297,8 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
     if (rc != CL4_OK) return rc;
     if (B == 0) return CL4_OK;
     CL4_REQUIRE(img && mask_in && mask_out && mask_in != mask_out, CL4_EINVAL, "pamr_forward: null or aliased pointers");
+    CL4_REQUIRE((((uintptr_t)img | (uintptr_t)mask_in | (uintptr_t)mask_out | (uintptr_t)scratch) & 15) == 0, CL4_EINVAL,
+                "pamr_forward: img, mask_in, mask_out and scratch must be 16-byte aligned (128-bit loads, TMA)");
     const size_t HW = (size_t)H * W;
     cudaStream_t s = (cudaStream_t)stream;
     auto record = [&](cl4_event_t ev) -> int {

@@ -131,7 +131,10 @@ def _as_f32(t, name):
     _lib.require_cuda(t, name)
     if t.dtype != torch.float32:
         raise TypeError(f"{name} must be float32 (got {t.dtype}); run PAMR outside autocast (SURVEY D4)")
-    return t.detach().contiguous()
+    t = t.detach().contiguous()
+    if t.data_ptr() % 16:  # a contiguous view at an odd storage offset: the kernels use 128-bit loads and TMA (16-byte bases)
+        t = t.clone()
+    return t
 
 
 def pamr_forward(x, mask, num_iter, dilations):

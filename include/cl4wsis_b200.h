@@ -85,6 +85,7 @@ int cl4_pamr_sweep(const float* w, const float* mask_in, float* mask_out, int B,
  * img [B,K,H,W], mask_in [B,C,H,W] -> mask_out [B,C,H,W].  scratch must hold
  * cl4_pamr_scratch_bytes(...) bytes (weights [B,8D,H,W] + up to two replicate-padded
  * mask buffers [B*C,H+48,W+48]).  mask_in is not modified; mask_out may not alias it.
+ * img, mask_in, mask_out and scratch must be 16-byte aligned (128-bit loads, TMA), else CL4_EINVAL.
  * The _timed variant additionally records the two (nullable) events on `stream`
  * around the num_iter propagation sweeps, for per-kernel timing. */
 size_t cl4_pamr_scratch_bytes(int B, int K, int C, int H, int W, int D, int num_iter);

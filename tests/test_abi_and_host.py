@@ -62,6 +62,11 @@ def test_argument_validation_returns_codes_without_a_gpu(lib):
     assert lib.cl4_peak_extract(null, null, null, null, null, 0, 1, 1, 8, 8, 3, 65, null) == _lib.CL4_EINVAL
     assert lib.cl4_peak_extract(null, null, null, null, null, 0, 1, 1, 64, 64, 3, 300, null) == _lib.CL4_EUNSUPPORTED
     assert lib.cl4_group_pixels(null, null, 1, 1, null, null, null, 1, 8, 8, 0, null) == _lib.CL4_EINVAL
+    # misaligned buffers are refused before anything is launched (128-bit loads, TMA)
+    v = ctypes.c_void_p
+    assert lib.cl4_pamr_forward(v(0x1004), v(0x2000), v(0x3000), v(0x4000), 1 << 40, 1, 3, 2, 64, 64, _lib.int_array([1, 2, 4, 8, 12, 24]),
+                                6, 10, null) == _lib.CL4_EINVAL
+    assert b"16-byte aligned" in lib.cl4_last_error()
     with pytest.raises(ValueError):
         _lib.check(_lib.CL4_EINVAL, "x")
     with pytest.raises(NotImplementedError):
