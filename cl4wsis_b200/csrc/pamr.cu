@@ -217,7 +217,7 @@ static int make_dilations(const int* dilations, int D, Dilations* out) {
 
 // weights region of the scratch: large enough for either tiled layout
 static size_t weight_scratch_elems(int B, int H, int W, int D) {
-    const size_t a = tiled_weight_elems(B, H, W, D), b = (D == 6) ? lattice_weight_elems(B, H, W) : 0;
+    const size_t a = tiled_weight_elems(B, H, W, D), b = (D == 6 || D == 5) ? lattice_weight_elems(B, H, W) : 0;
     return a > b ? a : b;
 }
 
@@ -342,7 +342,7 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
     if (use_lattice) {
         float* pimg = reinterpret_cast<float*>(base + wbytes + (num_iter >= 2 ? 2 : 1) * padded);
         rc = launch_pad_copy(img, pimg, (long long)B * K, H, W, s);
-        if (rc == CL4_OK) rc = launch_weights_lattice(pimg, wts, B, K, H, W, s);
+        if (rc == CL4_OK) rc = launch_weights_lattice(pimg, wts, B, K, H, W, D, s);
     } else if (use_tma && weights_tma_applicable(K)) {
         // image -> replicate-padded copy (scratch, after the mask buffers) -> TMA-staged weights kernel
         float* pimg = reinterpret_cast<float*>(base + wbytes + (num_iter >= 2 ? 2 : 1) * padded);
@@ -366,7 +366,7 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
         for (int it = 0; it < num_iter; ++it) {
             const bool last = (it == num_iter - 1);
             float* dst = last ? mask_out : nxt;
-            rc = launch_sweep_lattice(wts, cur, cur_pitch, cur_plane, dst, last ? W : sp, last ? (long long)H * W : splane, B, C, H, W, s);
+            rc = launch_sweep_lattice(wts, cur, cur_pitch, cur_plane, dst, last ? W : sp, last ? (long long)H * W : splane, B, C, H, W, D, s);
             if (rc != CL4_OK) return rc;
             cur = dst;
             cur_pitch = sp;

@@ -22,15 +22,15 @@ int launch_weights_tma(const float* padded_img, float* w, int B, int K, int H, i
 int launch_sweep_tma(const float* w, const float* padded_in, float* out, int out_padded, int B, int C, int H, int W,
                      const Dilations& dil, int D, cudaStream_t s);
 
-// Lattice sweep for the dilation set [1,2,4,8,12,24] (pamr_lattice.cu): three warp groups, one per dilation
+// Lattice sweep for the dilation sets [1,2,4,8,12,24] and [1,2,4,8,12] (pamr_lattice.cu): three warp groups, one per dilation
 // pair {d, 2d}; 24 x 48 tiles; weights in its own thread-major layout (lattice_weight_elems).
 bool sweep_lattice_applicable(int K, int H, int W, const Dilations& dil, int D);
 size_t lattice_weight_elems(int B, int H, int W);
-int launch_weights_lattice(const float* padded_img, float* w, int B, int K, int H, int W, cudaStream_t s);
+int launch_weights_lattice(const float* padded_img, float* w, int B, int K, int H, int W, int D, cudaStream_t s);
 // in / out: planes of H x W pixels, rows `pitch` and planes `plane` elements apart (the replicate padding happens
 // inside the kernel's shared-memory ring; nothing around the image area is read or written)
 int launch_sweep_lattice(const float* w, const float* in, int in_pitch, long long in_plane, float* out, int out_pitch,
-                         long long out_plane, int B, int C, int H, int W, cudaStream_t s);
+                         long long out_plane, int B, int C, int H, int W, int D, cudaStream_t s);
 
 // All iterations on-chip for maps up to 64 x 64 (pamr_fused.cu): D <= 6, every dilation <= 24.
 // w: tile-major weights; mask_in / mask_out: plain [B*C][H][W]; num_iter >= 1.

@@ -1,5 +1,6 @@
 // PAMR propagation sweep, "lattice" variant for the dilation set [1,2,4,8,12,24]
-// (PAMR's class default, reference wss/modules.py:125; the sweep itself is :148-149).
+// (PAMR's class default, reference wss/modules.py:125; the sweep itself is :148-149) and for the
+// trainer's [1,2,4,8,12] (train.py:81; kFar = false: group B without its dilation-24 part).
 //
 // Why.  The TMA sweep in pamr_tma.cu is bound by shared-memory bandwidth: every FMA needs one
 // weight (reused across the C classes -> registers) and one source value (reused only across
@@ -117,9 +118,12 @@ __device__ __forceinline__ void load_weight_group(float (&w)[kLW], const float4*
     w[4 * g + 2] = v.z;
     w[4 * g + 3] = v.w;
 }
+// kSkipFar: group B without dilation 24 (the trainer's set [1,2,4,8,12]) leaves taps 16..23 of every slot unused
+template <bool kSkipFar>
 __device__ __forceinline__ void load_weights(float (&w)[kLW], const float4* __restrict__ wp) {
 #pragma unroll
-    for (int g = 0; g < kLW / 4; ++g) load_weight_group(w, wp, g);
+    for (int g = 0; g < kLW / 4; ++g)
+        if (!kSkipFar || (g % (kLTaps / 4)) < 4) load_weight_group(w, wp, g);
 }
 
 // One source value `v` at lattice position (r, c) of an A x B block whose taps are the steps 1..NS of the
@@ -202,7 +206,7 @@ __device__ __forceinline__ void group_a_pair_class(float (&w)[kLW], float (&acc)
 // group B: 4 x 2 block of adjacent pixels.  Dilations 1 and 2 (steps 1, 2 of the unit lattice): rows -2..5,
 // columns -2..3 as float2.  Dilation 24 (third tap set, weights slot*24 + 16 + tap): the two pixels of a row
 // share one float2 per tap.
-template <bool kReload>
+template <bool kReload, bool kFar>
 __device__ __forceinline__ void group_b_class(float (&w)[kLW], float (&acc)[kLPx], const float* __restrict__ sp,
                                               const float4* __restrict__ nw) {
 #pragma unroll
@@ -213,6 +217,7 @@ __device__ __forceinline__ void group_b_class(float (&w)[kLW], float (&acc)[kLPx
             feed<4, 2, 2, kReload>(w, acc, v.x, r, c, nw);
             feed<4, 2, 2, kReload>(w, acc, v.y, r, c + 1, nw);
         }
+    if (kFar) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -229,6 +234,7 @@ __device__ __forceinline__ void group_b_class(float (&w)[kLW], float (&acc)[kLPx
                     load_weight_group(w, nw, k1 >> 2);
                 }
             }
+    }
 }
 
 struct LatticeOut {
@@ -371,7 +377,7 @@ __device__ __forceinline__ void lattice_patcher(const LatticeCtx& cx) {
 
 // The item loop of one warp group (G = 0: A, G = 1: B).  Item i of this CTA is (tile ordinal, class) =
 // ((i + s0) / C mod n_my, (i + s0) mod C) as in pamr_tma.cu (staggered class phase).
-template <int G>
+template <int G, bool kFar>
 __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const LatticeOut& out) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int tg = tid - G * kLGroupThreads;
@@ -432,7 +438,7 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
     if (cx.total > 0) {
         enter_tile(0);
         prefetch_next_weights(0);
-        load_weights(w, weight_ptr(blockIdx.x));
+        load_weights<(G == 1 && !kFar)>(w, weight_ptr(blockIdx.x));
     }
 
     // loop state kept incrementally (no division per item): ring stage + phase, partial buffer + phase,
@@ -472,8 +478,8 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
             if (reload) group_a_class<true>(w, acc, sp, nw);
             else group_a_class<false>(w, acc, sp, nw);
         } else {
-            if (reload) group_b_class<true>(w, acc, sp, nw);
-            else group_b_class<false>(w, acc, sp, nw);
+            if (reload) group_b_class<true, kFar>(w, acc, sp, nw);
+            else group_b_class<false, kFar>(w, acc, sp, nw);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive_u32(empty0 + 8u * stage);  // this warp no longer reads the window
@@ -553,6 +559,7 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
     }
 }
 
+template <bool kFar>  // kFar: dilation 24 present ([1,2,4,8,12,24]); otherwise [1,2,4,8,12]
 __global__ void __launch_bounds__(kLLaunchThreads, 1)
 pamr_sweep_lattice_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wts, LatticeOut out, int C,
                           int H, int W, int tiles_x, int tiles_y, int n_tiles) {
@@ -606,8 +613,8 @@ pamr_sweep_lattice_kernel(const __grid_constant__ CUtensorMap tmap, const float*
 #ifdef CL4_LATTICE_ONLY  // ablation: only one group runs (needs NOTMA + NOHANDOVER)
     if ((threadIdx.x < kLGroupThreads) != (CL4_LATTICE_ONLY == 0)) return;
 #endif
-    if (threadIdx.x < kLGroupThreads) lattice_group<0>(cx, out);  // warp-uniform
-    else lattice_group<1>(cx, out);
+    if (threadIdx.x < kLGroupThreads) lattice_group<0, kFar>(cx, out);  // warp-uniform
+    else lattice_group<1, kFar>(cx, out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -615,11 +622,11 @@ pamr_sweep_lattice_kernel(const __grid_constant__ CUtensorMap tmap, const float*
 // image: one CTA per 32 x 32 tile, the K (<= 3) 80 x 84 channel windows arrive by TMA, each thread
 // walks four pixels (lanes along x: conflict-free LDS at immediate offsets).
 // ---------------------------------------------------------------------------------------------
+template <int D, class DS>
 __global__ void __launch_bounds__(kLThreads, 2)
 pamr_weights_lattice_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ wts, int K, int tiles_x,
                             int tiles_per_img) {
-    constexpr int D = 6, P = 48;
-    using DS = DilVoc6;
+    constexpr int P = 8 * D;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* win = reinterpret_cast<float*>(smem_raw);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)3 * kLStageBytes);
@@ -696,16 +703,19 @@ pamr_weights_lattice_kernel(const __grid_constant__ CUtensorMap tmap, float* __r
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             pb[q * kLThreads] = make_float4(logit[4 * q] * rz, logit[4 * q + 1] * rz, logit[4 * q + 2] * rz, logit[4 * q + 3] * rz);
+        if (D == 6) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
-            pb[(4 + q) * kLThreads] = make_float4(logit[40 + 4 * q] * rz, logit[41 + 4 * q] * rz, logit[42 + 4 * q] * rz, logit[43 + 4 * q] * rz);
+            for (int q = 0; q < 2; ++q)
+                pb[(4 + q) * kLThreads] = make_float4(logit[P - 8 + 4 * q] * rz, logit[P - 7 + 4 * q] * rz, logit[P - 6 + 4 * q] * rz,
+                                                      logit[P - 5 + 4 * q] * rz);
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------ host
 bool sweep_lattice_applicable(int K, int H, int W, const Dilations& dil, int D) {
-    if (D != 6 || K < 1 || K > 3) return false;
-    for (int i = 0; i < 6; ++i)
+    if ((D != 6 && D != 5) || K < 1 || K > 3) return false;
+    for (int i = 0; i < D; ++i)  // [1,2,4,8,12,24] (class default) or its first five (the trainer's set, train.py:81)
         if (dil.d[i] != DilVoc6::get(i)) return false;
     if (W % 4 != 0) return false;                   // TMA: 16-byte global row pitch; float2 stores
     if ((long long)H * W <= 64 * 64) return false;  // small maps: the fused kernel
@@ -716,7 +726,20 @@ size_t lattice_weight_elems(int B, int H, int W) {
     return (size_t)B * ceil_div(H, kTile) * ceil_div(W, kTile) * (size_t)kLWeightsPerTile;
 }
 
-int launch_weights_lattice(const float* padded_img, float* w, int B, int K, int H, int W, cudaStream_t s) {
+template <int D, class DS>
+static int launch_weights_lattice_t(const CUtensorMap& tmap, float* w, int K, int tiles_x, int tiles_y, int n_tiles, cudaStream_t s) {
+    auto kern = pamr_weights_lattice_kernel<D, DS>;
+    const size_t smem = (size_t)3 * kLStageBytes + 64;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("pamr_weights_lattice: smem attribute: %s", cudaGetErrorString(e));
+        return CL4_ECUDA;
+    }
+    kern<<<n_tiles, kLThreads, smem, s>>>(tmap, w, K, tiles_x, tiles_x * tiles_y);
+    return check_launch("pamr_weights_lattice");
+}
+
+int launch_weights_lattice(const float* padded_img, float* w, int B, int K, int H, int W, int D, cudaStream_t s) {
     CUtensorMap tmap;
     const int rc = encode_tmap_3d_f32(&tmap, padded_img, W + 2 * kHalo, H + 2 * kHalo, (long long)B * K, kLPitch, kBox);
     if (rc != 0) {
@@ -725,18 +748,12 @@ int launch_weights_lattice(const float* padded_img, float* w, int B, int K, int 
     }
     const int tiles_x = ceil_div(W, kTile), tiles_y = ceil_div(H, kTile);
     const int n_tiles = B * tiles_x * tiles_y;
-    const size_t smem = (size_t)3 * kLStageBytes + 64;
-    cudaError_t e = cudaFuncSetAttribute(pamr_weights_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        set_error("pamr_weights_lattice: smem attribute: %s", cudaGetErrorString(e));
-        return CL4_ECUDA;
-    }
-    pamr_weights_lattice_kernel<<<n_tiles, kLThreads, smem, s>>>(tmap, w, K, tiles_x, tiles_x * tiles_y);
-    return check_launch("pamr_weights_lattice");
+    return D == 6 ? launch_weights_lattice_t<6, DilVoc6>(tmap, w, K, tiles_x, tiles_y, n_tiles, s)
+                  : launch_weights_lattice_t<5, DilVoc5>(tmap, w, K, tiles_x, tiles_y, n_tiles, s);
 }
 
 int launch_sweep_lattice(const float* w, const float* in, int in_pitch, long long in_plane, float* out, int out_pitch,
-                         long long out_plane, int B, int C, int H, int W, cudaStream_t s) {
+                         long long out_plane, int B, int C, int H, int W, int D, cudaStream_t s) {
     CUtensorMap tmap;  // over the H x W image area of each plane; boxes may start at negative coordinates (zero fill)
     const int rc = encode_tmap_3d_f32_strided(&tmap, in, W, H, (long long)B * C, in_pitch, in_plane, kLPitch, kBox);
     if (rc != 0) {
@@ -749,13 +766,14 @@ int launch_sweep_lattice(const float* w, const float* in, int in_pitch, long lon
     so.pitch = out_pitch;
     const int tiles_x = ceil_div(W, kTile), tiles_y = ceil_div(H, kTile);
     const int n_tiles = B * tiles_x * tiles_y;
-    cudaError_t e = cudaFuncSetAttribute(pamr_sweep_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmem);
+    auto kern = D == 6 ? pamr_sweep_lattice_kernel<true> : pamr_sweep_lattice_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmem);
     if (e != cudaSuccess) {
         set_error("pamr_sweep_lattice: smem attribute: %s", cudaGetErrorString(e));
         return CL4_ECUDA;
     }
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-    pamr_sweep_lattice_kernel<<<grid, kLLaunchThreads, kLSmem, s>>>(tmap, w, so, C, H, W, tiles_x, tiles_y, n_tiles);
+    kern<<<grid, kLLaunchThreads, kLSmem, s>>>(tmap, w, so, C, H, W, tiles_x, tiles_y, n_tiles);
     return check_launch("pamr_sweep_lattice");
 }
 

@@ -39,7 +39,7 @@ class PseudoLabelStep:
         # launches per step.  Lattice sweep (class-default dilations, the replicate padding happens inside the kernel):
         # image pad, weights, num_iter sweeps, 2 NMS, grouping.  4-pixel TMA sweep: + mask pad and num_iter-1 frame rewrites.
         import os
-        lattice = (self.dil == [1, 2, 4, 8, 12, 24] and K <= 3 and W % 4 == 0 and H * W > 64 * 64
+        lattice = (self.dil in ([1, 2, 4, 8, 12, 24], [1, 2, 4, 8, 12]) and K <= 3 and W % 4 == 0 and H * W > 64 * 64
                    and os.environ.get("CL4_SWEEP") in (None, "", "lattice"))
         self.launches_per_step = (1 + 1 + self.num_iter + 2 + 1 if lattice
                                   else 1 + 1 + 1 + self.num_iter + max(self.num_iter - 1, 0) + 2 + 1)

@@ -124,11 +124,11 @@ def test_pamr_small_map_paths_agree(cl4, oracle, monkeypatch, path, B, C, H, W, 
     (1, 1, 72, 68, 1),       # single class, single iteration: straight to the output
     (5, 30, 160, 160, 2),    # 125 tiles x 30 classes: every CTA switches tiles (weight reload on the fly)
 ])
-def test_pamr_lattice_sweep(cl4, oracle, monkeypatch, mode, B, C, H, W, T):
+@pytest.mark.parametrize("dil", [[1, 2, 4, 8, 12, 24], [1, 2, 4, 8, 12]])
+def test_pamr_lattice_sweep(cl4, oracle, monkeypatch, mode, dil, B, C, H, W, T):
     """The two-group lattice sweep (pamr_lattice.cu) and the 4-pixel TMA sweep on the class-default dilation set
-    (wss/modules.py:125), each against the oracle."""
+    (wss/modules.py:125) and on the trainer's (train.py:81), each against the oracle."""
     monkeypatch.setenv("CL4_SWEEP", mode)
-    dil = [1, 2, 4, 8, 12, 24]
     rng = np.random.default_rng(B * 1000 + C * 100 + H + W)
     x = (rng.integers(0, 256, (B, 3, H, W)) / 255.0).astype(np.float32)
     m = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).softmax(1).numpy()
