@@ -580,7 +580,11 @@ pamr_sweep_lattice_kernel(const __grid_constant__ CUtensorMap tmap, const float*
     cx.tiles_per_img = tiles_x * tiles_y;
     cx.n_my = (n_tiles > (int)blockIdx.x) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     cx.total = cx.n_my * C;
+#ifdef CL4_LATTICE_NOSTAGGER  // experiment: every CTA starts its first tile at class 0
+    cx.s0 = 0;
+#else
     cx.s0 = (int)(((long long)blockIdx.x * C) / gridDim.x);
+#endif
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap);
