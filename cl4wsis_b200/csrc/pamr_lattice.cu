@@ -112,7 +112,7 @@ __host__ __device__ constexpr bool is_tap(int di, int dj, int s) {
 
 // The thread's 192 weights of a tile: 48 float4 at [k/4][thread].
 __device__ __forceinline__ void load_weight_group(float (&w)[kLW], const float4* __restrict__ wp, const int g) {
-    const float4 v = __ldg(wp + g * kLThreads);
+    const float4 v = __ldg(wp + g * kLThreads);  // (evict-first loads measured slower once the L2 prefetch is off)
     w[4 * g + 0] = v.x;
     w[4 * g + 1] = v.y;
     w[4 * g + 2] = v.z;
@@ -411,7 +411,12 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
         if (nn == kk) return;
         const float* base = cx.wts + (size_t)(blockIdx.x + nn * gridDim.x) * kLWeightsPerTile;
         constexpr int kChunk = kLWeightsPerTile * 4 / 8;  // 24576 bytes, one per warp
+#ifdef CL4_LATTICE_PREFETCH_WEIGHTS  // off: the bulk L2 prefetch of the next tile's 196 KB cost 3 % (0.482 -> 0.467 ms without)
         if (lane == 0) bulk_prefetch_l2(reinterpret_cast<const char*>(base) + (size_t)(tid >> 5) * kChunk, kChunk);
+#else
+        (void)base;
+        (void)kChunk;
+#endif
     };
 
     int k = 0, c = cx.s0;
@@ -519,7 +524,9 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
                     float2 r;
                     r.x = acc[2 * i] + a.x;
                     r.y = acc[2 * i + 1] + a.y;
-                    if (i < nrows) *reinterpret_cast<float2*>(oc + (long long)i * out.pitch) = r;
+                    // the output is not read again before the next sweep: evict-first stores keep L2 for windows and
+                    // weights (0.482 -> 0.481 ms; 0.467 -> 0.464 together with the prefetch change below)
+                    if (i < nrows) __stcs(reinterpret_cast<float2*>(oc + (long long)i * out.pitch), r);
                 }
             } else {
 #pragma unroll
