@@ -39,6 +39,9 @@ namespace cl4 {
 #ifndef CL4_SWEEP_AHEAD
 #define CL4_SWEEP_AHEAD (CL4_SWEEP_STAGES - 1)
 #endif
+#ifndef CL4_SWEEP_PREFETCH_WEIGHTS
+#define CL4_SWEEP_PREFETCH_WEIGHTS 0  // bulk L2 prefetch of the next tile's weights: off, it costs 1.6 % here (0.612 -> 0.602 ms) and 3 % in the lattice kernel
+#endif
 #ifndef CL4_SWEEP_L2_AHEAD
 #define CL4_SWEEP_L2_AHEAD 0
 #endif
@@ -208,15 +211,20 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
             if (x < W && tc.y0 + ty + i * kRowGap < H) valid |= 1u << i;
         o = out.ptr + (long long)tc.b * C * out.plane + (long long)(tc.y0 + ty) * out.pitch + x;
     };
-    // Pull the weights of the tile after tile ordinal kk (196 KB, contiguous) into L2 while tile kk
-    // is being processed, so that the on-the-fly refill hits L2 instead of HBM.
+    // (Optional, off by default.)  Pull the weights of the tile after tile ordinal kk (196 KB, contiguous) into L2
+    // while tile kk is being processed, so that the on-the-fly refill hits L2 instead of HBM.
     auto prefetch_next_weights = [&](int kk) {
         int nn = kk + 1;
         if (nn == n_my) nn = 0;
         if (nn == kk) return;
         const float* base = wts + (size_t)(blockIdx.x + nn * gridDim.x) * (P * kTile * kTile);
         constexpr int kChunk = P * kTile * kTile * 4 / 8;  // 8 chunks, issued by 8 different warps
+#if CL4_SWEEP_PREFETCH_WEIGHTS
         if (lane == 0) bulk_prefetch_l2(reinterpret_cast<const char*>(base) + (size_t)wrp * kChunk, kChunk);
+#else
+        (void)base;
+        (void)kChunk;
+#endif
     };
     if (total > 0) {  // first tile: plain weight fetch
         enter_tile(0);
