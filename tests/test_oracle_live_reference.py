@@ -60,3 +60,46 @@ def test_center_nms_random(ref, oracle):
         heat = np.round(heat * 64) / 64  # exact ties
         want = mu.find_instance_center(torch.from_numpy(heat[None, None].copy()), thr, k, None).numpy()
         assert np.array_equal(oracle.find_instance_center(heat[None, None], thr, k), want)
+
+
+def test_phase1_pieces_random_shapes(ref):
+    """oracle/phase1.py against the reference's own `denorm` (utils/utils.py:26-41) and `pseudo_gtmask`
+    (wss/single_stage.py:18-40) function bodies, and against torch's interpolate / softmax, on random shapes incl.
+    all-equal planes (max ties), NaN-free extremes and every cutoff branch."""
+    import importlib.util
+    import torch
+    import torch.nn.functional as F
+    from oracle import phase1 as p1
+    spec = importlib.util.spec_from_file_location(
+        "make_golden_more", os.path.join(os.path.dirname(__file__), "golden", "make_golden_more.py"))
+    mm = importlib.util.module_from_spec(spec)
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    try:
+        spec.loader.exec_module(mm)
+    finally:
+        sys.path.remove(os.path.join(os.path.dirname(__file__), "golden"))
+        if REF in sys.path:
+            sys.path.remove(REF)
+    denorm = mm._ref_function("utils/utils.py", "denorm")
+    pseudo_gtmask = mm._ref_function("wss/single_stage.py", "pseudo_gtmask")
+    rng = np.random.default_rng(17)
+    for (B, C, Hi, Wi, h, w) in [(2, 4, 40, 56, 10, 14), (1, 21, 64, 64, 32, 32), (3, 2, 9, 11, 9, 11), (1, 5, 33, 17, 2, 3)]:
+        img = rng.standard_normal((B, 3, Hi, Wi)).astype(np.float32)
+        assert np.array_equal(p1.denorm(img), denorm(torch.from_numpy(img)).numpy())
+        assert np.array_equal(p1.denorm(img[0]), denorm(torch.from_numpy(img[0])).numpy())      # the [3,H,W] branch
+        raw = p1.denorm(img)
+        want = F.interpolate(torch.from_numpy(raw), (h, w), mode="bilinear", align_corners=True).numpy()
+        np.testing.assert_allclose(p1.resize_bilinear_ac(raw, (h, w)), want, rtol=2e-6, atol=1e-6)
+        logits = (4 * rng.standard_normal((B, C, h, w))).astype(np.float32)
+        soft = torch.from_numpy(logits).softmax(1).numpy()
+        np.testing.assert_allclose(p1.softmax_channels(logits), soft, rtol=2e-6, atol=1e-9)
+        l1h = (rng.random((B, C - 1)) < 0.5).astype(np.float32)
+        gated = p1.gate_labels(soft, l1h)
+        g2 = torch.from_numpy(soft.copy())
+        g2[:, 1:] *= torch.from_numpy(l1h)[:, :, None, None]
+        assert np.array_equal(gated, g2.numpy())
+        gated[0, -1] = 0.25                      # a constant plane: nothing exceeds its own scaled maximum
+        for amb, top, bkg, low in [(True, 0.6, 0.7, 0.2), (False, 0.6, 0.6, 0.2), (True, 0.9, 0.1, 0.0), (True, 0.3, 0.3, 0.9)]:
+            want = pseudo_gtmask(torch.from_numpy(gated.copy()), ambiguous=amb, cutoff_top=top, cutoff_bkg=bkg, cutoff_low=low).numpy()
+            assert np.array_equal(p1.pseudo_gtmask(gated, amb, top, bkg, low), want), (B, C, amb, top, bkg, low)
