@@ -221,6 +221,12 @@ static size_t weight_scratch_elems(int B, int H, int W, int D) {
     return a > b ? a : b;
 }
 
+// one ping-pong mask buffer of the scratch: replicate-padded planes (4-pixel sweep) or pair cells (duo sweep), whichever is larger
+static size_t mask_buffer_bytes(int B, int C, int H, int W) {
+    const size_t a = (size_t)B * C * padded_plane_elems(H, W), b = duo_buffer_elems(B, C, H, W);
+    return align_up(sizeof(float) * (a > b ? a : b), 256);
+}
+
 static int check_plane(const char* what, long long B, int H, int W) {
     CL4_REQUIRE(B >= 0 && H > 0 && W > 0, CL4_EINVAL, "%s: bad shape", what);
     CL4_REQUIRE((long long)H * W < (1ll << 30), CL4_EUNSUPPORTED, "%s: plane too large", what);
@@ -278,7 +284,7 @@ extern "C" size_t cl4_pamr_scratch_bytes(int B, int K, int C, int H, int W, int 
     const size_t wbytes = cl4::align_up(sizeof(float) * cl4::weight_scratch_elems(B, H, W, D), 256);
     // padded path: one replicate-padded copy of the input (+ a second ping-pong buffer from 2 sweeps on);
     // generic path: one plain ping-pong buffer.  The padded layout is the larger of the two.
-    const size_t padded = cl4::align_up(sizeof(float) * (size_t)B * C * cl4::padded_plane_elems(H, W), 256);
+    const size_t padded = cl4::mask_buffer_bytes(B, C, H, W);
     const size_t padded_img = cl4::align_up(sizeof(float) * (size_t)B * K * cl4::padded_plane_elems(H, W), 256);
     return wbytes + (num_iter >= 2 ? 2 : 1) * padded + padded_img;
 }
@@ -318,7 +324,7 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
     char* base = reinterpret_cast<char*>(scratch);
     float* wts = reinterpret_cast<float*>(base);
     const size_t wbytes = align_up(sizeof(float) * weight_scratch_elems(B, H, W, D), 256);
-    const size_t padded = align_up(sizeof(float) * (size_t)B * C * padded_plane_elems(H, W), 256);
+    const size_t padded = mask_buffer_bytes(B, C, H, W);
     float* bufA = reinterpret_cast<float*>(base + wbytes);
     float* bufB = reinterpret_cast<float*>(base + wbytes + padded);
     // CL4_SWEEP=v1 forces the register/L1 kernel, CL4_SWEEP=tma skips the fused small-map kernel
@@ -326,7 +332,8 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
     // CL4_SWEEP=lattice / nolattice: take / skip the lattice sweep (pamr_lattice.cu; the default wherever it applies)
     const char* force = getenv("CL4_SWEEP");
     const bool force_v1 = force && strcmp(force, "v1") == 0, force_tma = force && strcmp(force, "tma") == 0;
-    const bool force_lat = force && strcmp(force, "lattice") == 0, no_lat = force && strcmp(force, "nolattice") == 0;
+    const bool force_lat1 = force && strcmp(force, "lattice1") == 0;  // the one-class-per-window lattice sweep
+    const bool force_lat = force_lat1 || (force && strcmp(force, "lattice") == 0), no_lat = force && strcmp(force, "nolattice") == 0;
     if (!force_v1 && !force_tma && pamr_fused_applicable(H, W, dil, D)) {
         // small maps (the trainer's feature resolution): weights, then every iteration in one launch
         rc = dispatch_D<WeightsLauncher>(D, img, wts, B, K, H, W, dil, 1, s);
@@ -352,6 +359,21 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
         rc = dispatch_D<WeightsLauncher>(D, img, wts, B, K, H, W, dil, use_tma ? 1 : 0, s);
     }
     if (rc != CL4_OK) return rc;
+    if (use_lattice && !force_lat1) {
+        // class-pair sweep: pack the planar masks into pair cells, ping-pong A -> B -> A ..., the last sweep writes planar
+        if ((rc = record(ev_sweeps_begin)) != CL4_OK) return rc;
+        rc = launch_duo_pack(mask_in, bufA, B, C, H, W, s);
+        if (rc != CL4_OK) return rc;
+        float* cur = bufA;
+        float* nxt = bufB;
+        for (int it = 0; it < num_iter; ++it) {
+            const bool last = (it == num_iter - 1);
+            rc = launch_sweep_duo(wts, cur, last ? mask_out : nxt, last ? 1 : 0, B, C, H, W, D, s);
+            if (rc != CL4_OK) return rc;
+            float* t = cur; cur = nxt; nxt = t;
+        }
+        return record(ev_sweeps_end);
+    }
     if (use_lattice) {
         // ping-pong in -> A -> B -> A ... -> out with no padding pass.  The scratch planes keep the (W + 48)-float row pitch
         // of the padded layout (a power-of-two pitch such as 2048 bytes makes the 80 rows of a window collide in the memory

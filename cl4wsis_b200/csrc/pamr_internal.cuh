@@ -22,8 +22,9 @@ int launch_weights_tma(const float* padded_img, float* w, int B, int K, int H, i
 int launch_sweep_tma(const float* w, const float* padded_in, float* out, int out_padded, int B, int C, int H, int W,
                      const Dilations& dil, int D, cudaStream_t s);
 
-// Lattice sweep for the dilation sets [1,2,4,8,12,24] and [1,2,4,8,12] (pamr_lattice.cu): three warp groups, one per dilation
-// pair {d, 2d}; 24 x 48 tiles; weights in its own thread-major layout (lattice_weight_elems).
+// Lattice sweep for the dilation sets [1,2,4,8,12,24] and [1,2,4,8,12] (pamr_lattice.cu): two compute warp groups owning
+// dilations {4,8,12} and {1,2,24} of a 32 x 32 tile + a producer warpgroup; weights in its own thread-major layout
+// (lattice_weight_elems).
 bool sweep_lattice_applicable(int K, int H, int W, const Dilations& dil, int D);
 size_t lattice_weight_elems(int B, int H, int W);
 int launch_weights_lattice(const float* padded_img, float* w, int B, int K, int H, int W, int D, cudaStream_t s);
@@ -31,6 +32,14 @@ int launch_weights_lattice(const float* padded_img, float* w, int B, int K, int 
 // inside the kernel's shared-memory ring; nothing around the image area is read or written)
 int launch_sweep_lattice(const float* w, const float* in, int in_pitch, long long in_plane, float* out, int out_pitch,
                          long long out_plane, int B, int C, int H, int W, int D, cudaStream_t s);
+
+// Class-pair ("duo") sweep for the same two dilation sets (pamr_duo.cu): the masks between sweeps are pair-interleaved cells
+// [B][ceil(C/2)][H][W + 48][2]; packed fp32 FMAs on both classes of a cell.  Weights: the lattice layout.
+int duo_pitch(int W);                                          // floats per row of a pair plane
+size_t duo_buffer_elems(int B, int C, int H, int W);           // floats per pair-cell buffer
+int launch_duo_pack(const float* mask_in, float* cells, int B, int C, int H, int W, cudaStream_t s);  // planar -> cells
+int launch_sweep_duo(const float* w, const float* cells_in, float* out, int out_planar, int B, int C, int H, int W, int D,
+                     cudaStream_t s);
 
 // All iterations on-chip for maps up to 64 x 64 (pamr_fused.cu): D <= 6, every dilation <= 24.
 // w: tile-major weights; mask_in / mask_out: plain [B*C][H][W]; num_iter >= 1.

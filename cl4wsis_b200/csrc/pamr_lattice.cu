@@ -37,98 +37,13 @@
 //           bank-conflict free; group B's half-warps read 16 adjacent float2.
 //   weights thread-major [tile][k/4][thread] float4, k = slot*24 + tap (written by pamr_weights_lattice_kernel):
 //           48 128-bit loads per thread, a warp's load is one 512-byte run; same size as the 32x32 tile-major layout.
-#include "common.cuh"
-#include "pamr_internal.cuh"
-#include "pamr_sweep.cuh"
-#include "tma.cuh"
+#include "pamr_lattice.cuh"
 
 namespace cl4 {
 
-#ifndef CL4_LATTICE_STAGES
-#define CL4_LATTICE_STAGES 4  // 3..6 measure within 3 %; 4 stages + 2 partial buffers is the fastest (0.506 ms)
-#endif
-
-constexpr int kLThreads = 256;                       // 8 compute warps: 0-3 group A, 4-7 group B
-constexpr int kLLaunchThreads = kLThreads + 128;     // + a producer warpgroup (its first thread feeds the TMA ring)
-constexpr int kLGroupThreads = 128;
-constexpr int kLPitch = 84;                          // window pitch in floats; 84 % 32 == 20
-constexpr int kLStageFloats = kBox * kLPitch;        // 80 rows x 84 columns = 6720
-constexpr int kLStageBytes = kLStageFloats * 4;      // 26880 = 210 * 128
-constexpr int kLStages = CL4_LATTICE_STAGES;
-constexpr int kLPartPitch = 36;                      // partial sums of group A: 32 rows x 36 floats (36 % 32 == 4)
-constexpr int kLPartFloats = kTile * kLPartPitch;    // 1152
-constexpr int kLPx = 8;                              // pixels per thread
-constexpr int kLTaps = 24;                           // taps per thread and pixel (three dilations)
-constexpr int kLW = kLPx * kLTaps;                   // 192 weight registers
-constexpr int kLWeightsPerTile = kLW * kLThreads;    // 49152 floats = 48 taps x 1024 pixels
-#ifndef CL4_LATTICE_PARTS
-#define CL4_LATTICE_PARTS 2
-#endif
-#ifndef CL4_LATTICE_APAIR
-#define CL4_LATTICE_APAIR 0
-#endif
-#ifndef CL4_LATTICE_FINISHER
-#define CL4_LATTICE_FINISHER 1
-#endif
-constexpr int kLFin = CL4_LATTICE_FINISHER;          // the group that adds the other's partial sums and stores (0: A, 1: B)
-static_assert(!CL4_LATTICE_APAIR || CL4_LATTICE_FINISHER == 1, "the pair variant of group A only hands over");
-constexpr int kLParts = CL4_LATTICE_PARTS;           // partial-sum buffers: how far group A may run ahead of group B
-constexpr size_t kLSmem = (size_t)kLStages * kLStageBytes + kLParts * kLPartFloats * 4 + (3 * kLStages + 8 * kLParts) * 8 + 64;
-
-// ---- who owns pixel (y, x) of a tile in each group: thread (0..127 within the group) and slot (0..7) ----
-struct Owner {
-    int thread, slot;
-};
-constexpr bool kLAPair = CL4_LATTICE_APAIR != 0;  // group A on pairs of adjacent columns (LDS.64) instead of single lattice columns
-#if CL4_LATTICE_APAIR
-// group A, pair variant: a thread owns rows y0, y0+4 x column pairs (x0, x0+1), (x0+4, x0+5), x0 in {0, 2}: a 2 x 2
-// lattice block of float2.  8 x 8 super-blocks of 8 threads; a warp = the four super-blocks of one 8-row band, its
-// half-warps take super-blocks {0, 2} / {1, 3} so that the 16 float2 of an LDS.64 fall into 16 different bank pairs
-// (window pitch 84, partial pitch 36).  slot = ((i*2 + j)*2 + e).
-__host__ __device__ inline Owner owner_a(int y, int x) {
-    const int sby = y >> 3, ry = y & 7, sbx = x >> 3, rx = x & 7;
-    const int lane = (sbx & 1) * 16 + (sbx >> 1) * 8 + (ry & 3) * 2 + ((rx & 3) >> 1);
-    return Owner{sby * 32 + lane, (((ry >> 2) * 2 + (rx >> 2)) * 2) + (rx & 1)};
-}
-#else
-// group A: 2 x 4 lattice blocks of spacing 4 inside 8 x 16 super-blocks (16 threads = 4 x 4 phases)
-__host__ __device__ inline Owner owner_a(int y, int x) {
-    const int sby = y >> 3, ry = y & 7, sbx = x >> 4, rx = x & 15;
-    return Owner{(sby * 2 + sbx) * 16 + (ry & 3) * 4 + (rx & 3), (ry >> 2) * 4 + (rx >> 2)};
-}
-#endif
-// group B: 4 x 2 blocks of adjacent pixels, 16 blocks per row of blocks (one half-warp)
-__host__ __device__ inline Owner owner_b(int y, int x) { return Owner{(y >> 2) * 16 + (x >> 1), (y & 3) * 2 + (x & 1)}; }
-
-// reference tap order (wss/modules.py:30-40): row-major over the 3x3 neighbourhood, centre skipped
-__host__ __device__ constexpr int tap_index(int dy, int dx) {
-    const int idx = (dy + 1) * 3 + (dx + 1);
-    return idx > 4 ? idx - 1 : idx;
-}
-// lattice offset (di, dj) in units of the spacing: is it a tap of step s (dilation s * spacing)?
-__host__ __device__ constexpr bool is_tap(int di, int dj, int s) {
-    return (di == -s || di == 0 || di == s) && (dj == -s || dj == 0 || dj == s) && !(di == 0 && dj == 0);
-}
-
-// The thread's 192 weights of a tile: 48 float4 at [k/4][thread].
-__device__ __forceinline__ void load_weight_group(float (&w)[kLW], const float4* __restrict__ wp, const int g) {
-    const float4 v = __ldg(wp + g * kLThreads);  // (evict-first loads measured slower once the L2 prefetch is off)
-    w[4 * g + 0] = v.x;
-    w[4 * g + 1] = v.y;
-    w[4 * g + 2] = v.z;
-    w[4 * g + 3] = v.w;
-}
-// kSkipFar: group B without dilation 24 (the trainer's set [1,2,4,8,12]) leaves taps 16..23 of every slot unused
-template <bool kSkipFar>
-__device__ __forceinline__ void load_weights(float (&w)[kLW], const float4* __restrict__ wp) {
-#pragma unroll
-    for (int g = 0; g < kLW / 4; ++g)
-        if (!kSkipFar || (g % (kLTaps / 4)) < 4) load_weight_group(w, wp, g);
-}
-
 // One source value `v` at lattice position (r, c) of an A x B block whose taps are the steps 1..NS of the
 // lattice: feed every (pixel, tap) that reads it.  Weight register of (pixel slot, step s, tap): slot*24 + (s-1)*8 + tap.
-template <int A, int B, int NS, bool kReload>
+template <int G, int A, int B, int NS, bool kReload>
 __device__ __forceinline__ void feed(float (&w)[kLW], float (&acc)[kLPx], const float v, const int r, const int c,
                                      const float4* __restrict__ nw) {
 #pragma unroll
@@ -143,18 +58,9 @@ __device__ __forceinline__ void feed(float (&w)[kLW], float (&acc)[kLPx], const 
                     acc[i * B + j] = fmaf(w[k], v, acc[i * B + j]);
                     // sources arrive in row-major order, so taps 3 and 7 are the last uses of their float4:
                     // refill it with the next tile's weights right away (kReload: last class of a tile)
-                    if (kReload && (k & 3) == 3) load_weight_group(w, nw, k >> 2);
+                    if (kReload && (k & 3) == 3) load_weight_group<G>(w, nw, k >> 2);
                 }
             }
-}
-
-template <int A, int B, int NS>
-__host__ __device__ constexpr bool source_needed(int r, int c) {
-    for (int i = 0; i < A; ++i)
-        for (int j = 0; j < B; ++j)
-            for (int s = 1; s <= NS; ++s)
-                if (is_tap(r - i, c - j, s)) return true;
-    return false;
 }
 
 // group A: 2 x 4 lattice block of spacing 4, dilations 4, 8, 12 = steps 1, 2, 3; sp points at the block's
@@ -168,38 +74,7 @@ __device__ __forceinline__ void group_a_class(float (&w)[kLW], float (&acc)[kLPx
         for (int c = -3; c < 4 + 3; ++c)
             if (source_needed<2, 4, 3>(r, c)) {
                 const float v = sp[r * 4 * kLPitch + c * 4];
-                feed<2, 4, 3, kReload>(w, acc, v, r, c, nw);
-            }
-}
-
-// group A, pair variant: a 2 x 2 lattice block of column pairs; every lattice position is one float2 whose halves feed
-// the two pixels of a pair.  56 of the 8 x 8 lattice positions are read (56 LDS.64 for 192 FMAs).
-template <bool kReload>
-__device__ __forceinline__ void group_a_pair_class(float (&w)[kLW], float (&acc)[kLPx], const float* __restrict__ sp,
-                                                   const float4* __restrict__ nw) {
-#pragma unroll
-    for (int r = -3; r < 2 + 3; ++r)
-#pragma unroll
-        for (int c = -3; c < 2 + 3; ++c)
-            if (source_needed<2, 2, 3>(r, c)) {
-                const float2 v = *reinterpret_cast<const float2*>(sp + r * 4 * kLPitch + c * 4);
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j)
-#pragma unroll
-                        for (int st = 1; st <= 3; ++st) {
-                            const int di = r - i, dj = c - j;
-                            if (is_tap(di, dj, st)) {
-                                const int k = ((i * 2 + j) * 2) * kLTaps + (st - 1) * 8 + tap_index(di / st, dj / st);
-                                acc[(i * 2 + j) * 2] = fmaf(w[k], v.x, acc[(i * 2 + j) * 2]);
-                                acc[(i * 2 + j) * 2 + 1] = fmaf(w[k + kLTaps], v.y, acc[(i * 2 + j) * 2 + 1]);
-                                if (kReload && (k & 3) == 3) {
-                                    load_weight_group(w, nw, k >> 2);
-                                    load_weight_group(w, nw, (k + kLTaps) >> 2);
-                                }
-                            }
-                        }
+                feed<0, 2, 4, 3, kReload>(w, acc, v, r, c, nw);
             }
 }
 
@@ -214,8 +89,8 @@ __device__ __forceinline__ void group_b_class(float (&w)[kLW], float (&acc)[kLPx
 #pragma unroll
         for (int c = -2; c < 4; c += 2) {
             const float2 v = *reinterpret_cast<const float2*>(sp + r * kLPitch + c);
-            feed<4, 2, 2, kReload>(w, acc, v.x, r, c, nw);
-            feed<4, 2, 2, kReload>(w, acc, v.y, r, c + 1, nw);
+            feed<1, 4, 2, 2, kReload>(w, acc, v.x, r, c, nw);
+            feed<1, 4, 2, 2, kReload>(w, acc, v.y, r, c + 1, nw);
         }
     if (kFar) {
 #pragma unroll
@@ -230,18 +105,12 @@ __device__ __forceinline__ void group_b_class(float (&w)[kLW], float (&acc)[kLPx
                 acc[i * 2] = fmaf(w[k0], v.x, acc[i * 2]);
                 acc[i * 2 + 1] = fmaf(w[k1], v.y, acc[i * 2 + 1]);
                 if (kReload && (k0 & 3) == 3) {
-                    load_weight_group(w, nw, k0 >> 2);
-                    load_weight_group(w, nw, k1 >> 2);
+                    load_weight_group<1>(w, nw, k0 >> 2);
+                    load_weight_group<1>(w, nw, k1 >> 2);
                 }
             }
     }
 }
-
-struct LatticeOut {
-    float* ptr;       // element (plane 0, y = 0, x = 0) of the output
-    long long plane;  // elements between planes
-    int pitch;        // elements between rows (even)
-};
 
 struct LatticeCtx {
     float* stage0;
@@ -250,19 +119,6 @@ struct LatticeCtx {
     const float* wts;
     int C, H, W, tiles_x, tiles_per_img, n_my, total, s0;
 };
-
-struct LTile {
-    int b, y0, x0;
-};
-__device__ __forceinline__ LTile ltile(int t, int tiles_x, int tiles_per_img) {
-    LTile tc;
-    tc.b = t / tiles_per_img;
-    const int r = t - tc.b * tiles_per_img;
-    const int tyi = r / tiles_x;
-    tc.y0 = tyi * kTile;
-    tc.x0 = (r - tyi * tiles_x) * kTile;
-    return tc;
-}
 
 // The producer: one thread of a third warpgroup walks the items of this CTA in order, waits until all eight compute
 // warps have released the stage it is about to refill, and issues the window's TMA box.  The compute groups never
@@ -319,11 +175,7 @@ __device__ __forceinline__ void lattice_patcher(const LatticeCtx& cx) {
     if (cx.total > 0) enter_tile(0);
     for (int item = 0; item < cx.total; ++item) {
         mbar_wait_relaxed(&cx.full[s], phase);  // suspended, not spinning
-#ifdef CL4_EXP_PATCH_NOWORK  // experiment: the ready handshake without the patching
-        if (false) {
-#else
         if (rv0 > 0 || rv1 < kBox || cv0 > 0 || cv1 < kLPitch) {
-#endif
             float* win = cx.stage0 + (size_t)s * kLStageFloats;
             const int t = pw * 32 + lane;  // 0..95
             // columns left / right of the image: one thread per valid window row, independent stores of one value
@@ -385,11 +237,7 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
 
     // thread geometry: tile-relative row / column of the thread's block origin
     int ry, rx;
-    if (G == 0 && kLAPair) {
-        const int ln = tg & 31, sbx = ((ln >> 3) & 1) * 2 + (ln >> 4);
-        ry = (tg >> 5) * 8 + ((ln >> 1) & 3);
-        rx = sbx * 8 + (ln & 1) * 2;
-    } else if (G == 0) {
+    if (G == 0) {
         const int sb = tg >> 4;
         ry = (sb >> 1) * 8 + ((tg >> 2) & 3);
         rx = (sb & 1) * 16 + (tg & 3);
@@ -403,62 +251,33 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
     float w[kLW];
     float acc[kLPx];
     auto weight_ptr = [&](int t) -> const float4* {
-        return reinterpret_cast<const float4*>(cx.wts + (size_t)t * kLWeightsPerTile) + tid;
+        return reinterpret_cast<const float4*>(cx.wts + (size_t)t * kLWeightsPerTile) + weight_thread_base(tid);
     };
-    auto prefetch_next_weights = [&](int kk) {
-        int nn = kk + 1;
-        if (nn == cx.n_my) nn = 0;
-        if (nn == kk) return;
-        const float* base = cx.wts + (size_t)(blockIdx.x + nn * gridDim.x) * kLWeightsPerTile;
-        constexpr int kChunk = kLWeightsPerTile * 4 / 8;  // 24576 bytes, one per warp
-#ifdef CL4_LATTICE_PREFETCH_WEIGHTS  // off: the bulk L2 prefetch of the next tile's 196 KB cost 3 % (0.482 -> 0.467 ms without)
-        if (lane == 0) bulk_prefetch_l2(reinterpret_cast<const char*>(base) + (size_t)(tid >> 5) * kChunk, kChunk);
-#else
-        (void)base;
-        (void)kChunk;
-#endif
-    };
-
     int k = 0, c = cx.s0;
-    // the finishing group stores the pixels: store pointer and validity of its pixels (B: number of valid rows of
-    // its 4 x 2 block; A: one bit per pixel of its 2 x 4 lattice block)
+    // group B stores the pixels: store pointer and number of valid rows of its 4 x 2 block
     float* o = nullptr;
     int nrows = 0;
     auto enter_tile = [&](int kk) {
-        if (G != kLFin) return;
+        if (G != 1) return;
         const LTile tc = ltile(blockIdx.x + kk * gridDim.x, cx.tiles_x, cx.tiles_per_img);
         const int y = tc.y0 + ry, x = tc.x0 + rx;
-        if (G == 1) {
-            nrows = (x < cx.W) ? min(max(cx.H - y, 0), 4) : 0;
-        } else {
-            nrows = 0;
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (y + 4 * i < cx.H && x + 4 * j < cx.W) nrows |= 1 << (i * 4 + j);
-        }
+        nrows = (x < cx.W) ? min(max(cx.H - y, 0), 4) : 0;
         o = out.ptr + (long long)tc.b * C * out.plane + (long long)y * out.pitch + x;
     };
     if (cx.total > 0) {
         enter_tile(0);
-        prefetch_next_weights(0);
-        load_weights<(G == 1 && !kFar)>(w, weight_ptr(blockIdx.x));
+        load_weights<G, (G == 1 && !kFar)>(w, weight_ptr(blockIdx.x));
     }
 
     // loop state kept incrementally (no division per item): ring stage + phase, partial buffer + phase,
     // window pointer, hand-over barrier of this warp pair
-#ifdef CL4_EXP_NOPATCH  // experiment: no border patching, consumers wait for the TMA directly (wrong borders)
-    const uint32_t full0 = smem_u32(cx.full), empty0 = smem_u32(cx.empty);
-#else
     const uint32_t full0 = smem_u32(cx.ready), empty0 = smem_u32(cx.empty);  // "full" for the compute warps = patched
-#endif
     const uint32_t pfull0 = smem_u32(cx.pfull) + 8u * ((tid >> 5) & 3), pempty0 = smem_u32(cx.pempty) + 8u * ((tid >> 5) & 3);
     int stage = 0, pb = 0;
     uint32_t full_phase = 0, part_phase = 0;
     const float* sp = cx.stage0 + tb;
     float* pp = cx.part + pbase;
-    float* oc = (G == kLFin) ? o + (long long)c * out.plane : nullptr;
+    float* oc = (G == 1) ? o + (long long)c * out.plane : nullptr;
 
     for (int item = 0; item < cx.total; ++item) {
         // last class of this tile visit and another tile follows: refill the weights on the fly
@@ -470,75 +289,48 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
             reload = (item + 1 < cx.total) && (nk != k);
             nw = weight_ptr(blockIdx.x + nk * gridDim.x);
         }
-#ifndef CL4_LATTICE_NOTMA
         mbar_wait_u32(full0 + 8u * stage, full_phase);
-#endif
 
 #pragma unroll
         for (int i = 0; i < kLPx; ++i) acc[i] = 0.f;
-        if (G == 0 && kLAPair) {
-            if (reload) group_a_pair_class<true>(w, acc, sp, nw);
-            else group_a_pair_class<false>(w, acc, sp, nw);
-        } else if (G == 0) {
+        if (G == 0) {
             if (reload) group_a_class<true>(w, acc, sp, nw);
             else group_a_class<false>(w, acc, sp, nw);
         } else {
             if (reload) group_b_class<true, kFar>(w, acc, sp, nw);
             else group_b_class<false, kFar>(w, acc, sp, nw);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive_u32(empty0 + 8u * stage);  // this warp no longer reads the window
-
-        // A's warp j and B's warp j own the same 8 rows of the tile, so the hand-over is per warp pair
-        if (G != kLFin) {
-#ifndef CL4_LATTICE_NOHANDOVER  // ablation: free-running groups (wrong results)
+        // A's warp j and B's warp j own the same 8 rows of the tile, so the hand-over is per warp pair.  The ring stage is
+        // released AFTER the stores of the accumulators, never right after the last FMA: a store needs the FMA results, which
+        // need every window load to have RETURNED, and a release-arrive stays below earlier stores.  Placed before them, the
+        // arrive can be scheduled above FMAs whose LDS are still in flight, and a fast refill then overwrites window rows that
+        // are still being read (found with the class-pair sweep: rare wrong rows at 1024 x 1024).
+        if (G == 0) {
             if (item >= kLParts) mbar_wait_u32(pempty0 + 32u * pb, part_phase ^ 1u);
-#endif
-            if (G == 0 && kLAPair) {
 #pragma unroll
-                for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
-                        *reinterpret_cast<float2*>(pp + i * 4 * kLPartPitch + j * 4) =
-                            make_float2(acc[(i * 2 + j) * 2], acc[(i * 2 + j) * 2 + 1]);
-            } else if (G == 0) {
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) pp[i * 4 * kLPartPitch + j * 4] = acc[i * 4 + j];
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    *reinterpret_cast<float2*>(pp + i * kLPartPitch) = make_float2(acc[2 * i], acc[2 * i + 1]);
-            }
+                for (int j = 0; j < 4; ++j) pp[i * 4 * kLPartPitch + j * 4] = acc[i * 4 + j];
             __syncwarp();
-            if (lane == 0) mbar_arrive_u32(pfull0 + 32u * pb);
-        } else {
-#ifndef CL4_LATTICE_NOHANDOVER
-            mbar_wait_u32(pfull0 + 32u * pb, part_phase);
-#endif
-            if (G == 1) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 a = *reinterpret_cast<const float2*>(pp + i * kLPartPitch);
-                    float2 r;
-                    r.x = acc[2 * i] + a.x;
-                    r.y = acc[2 * i + 1] + a.y;
-                    // the output is not read again before the next sweep: evict-first stores keep L2 for windows and
-                    // weights (0.482 -> 0.481 ms; 0.467 -> 0.464 together with the prefetch change below)
-                    if (i < nrows) __stcs(reinterpret_cast<float2*>(oc + (long long)i * out.pitch), r);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float r = acc[i * 4 + j] + pp[i * 4 * kLPartPitch + j * 4];
-                        if ((nrows >> (i * 4 + j)) & 1) oc[(long long)(4 * i) * out.pitch + 4 * j] = r;
-                    }
+            if (lane == 0) {
+                mbar_arrive_u32(pfull0 + 32u * pb);
+                mbar_arrive_u32(empty0 + 8u * stage);  // this warp no longer reads the window
             }
+        } else {
+            mbar_wait_u32(pfull0 + 32u * pb, part_phase);
+            float2 a[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float2*>(pp + i * kLPartPitch);
             __syncwarp();
             if (lane == 0) mbar_arrive_u32(pempty0 + 32u * pb);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                // the output is not read again before the next sweep: evict-first stores keep L2 for windows and weights
+                if (i < nrows)
+                    __stcs(reinterpret_cast<float2*>(oc + (long long)i * out.pitch), make_float2(acc[2 * i] + a[i].x, acc[2 * i + 1] + a[i].y));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_u32(empty0 + 8u * stage);  // this warp no longer reads the window
             oc += out.plane;
         }
 
@@ -559,9 +351,8 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
             if (nk != k) {
                 k = nk;
                 enter_tile(k);
-                prefetch_next_weights(k);
             }
-            if (G == kLFin) oc = o;
+            if (G == 1) oc = o;
         }
     }
 }
@@ -587,11 +378,7 @@ pamr_sweep_lattice_kernel(const __grid_constant__ CUtensorMap tmap, const float*
     cx.tiles_per_img = tiles_x * tiles_y;
     cx.n_my = (n_tiles > (int)blockIdx.x) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     cx.total = cx.n_my * C;
-#ifdef CL4_LATTICE_NOSTAGGER  // experiment: every CTA starts its first tile at class 0
-    cx.s0 = 0;
-#else
-    cx.s0 = (int)(((long long)blockIdx.x * C) / gridDim.x);
-#endif
+    cx.s0 = (int)(((long long)blockIdx.x * C) / gridDim.x);  // staggered class phase (worth 1.3 %, profiles/r01f_notes.md)
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap);
@@ -612,18 +399,11 @@ pamr_sweep_lattice_kernel(const __grid_constant__ CUtensorMap tmap, const float*
         // the CTA owns 384 x 168 registers; what this warpgroup gives back ((168 - 24) x 128) is exactly what the two
         // compute warpgroups take ((240 - 168) x 256) -- a larger value here would leave their setmaxnreg.inc waiting forever
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-#ifndef CL4_LATTICE_NOTMA  // ablation: compute on whatever the stages hold
         if (threadIdx.x == kLThreads) lattice_producer(cx, &tmap);
-#ifndef CL4_EXP_NOPATCH
         else if (threadIdx.x >= kLThreads + 32) lattice_patcher(cx);
-#endif
-#endif
         return;
     }
     asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
-#ifdef CL4_LATTICE_ONLY  // ablation: only one group runs (needs NOTMA + NOHANDOVER)
-    if ((threadIdx.x < kLGroupThreads) != (CL4_LATTICE_ONLY == 0)) return;
-#endif
     if (threadIdx.x < kLGroupThreads) lattice_group<0, kFar>(cx, out);  // warp-uniform
     else lattice_group<1, kFar>(cx, out);
 }
@@ -706,19 +486,20 @@ pamr_weights_lattice_kernel(const __grid_constant__ CUtensorMap tmap, float* __r
         const float rz = 1.f / z;
         // group A holds dilations 4, 8, 12 (taps 16..39), group B dilations 1, 2 (taps 0..15) and 24 (taps 40..47)
         const Owner oa = owner_a(y, x), ob = owner_b(y, x);
-        float4* pa = reinterpret_cast<float4*>(o) + (size_t)(oa.slot * (kLTaps / 4)) * kLThreads + oa.thread;
-        float4* pb = reinterpret_cast<float4*>(o) + (size_t)(ob.slot * (kLTaps / 4)) * kLThreads + kLGroupThreads + ob.thread;
+        float4* pa = reinterpret_cast<float4*>(o) + oa.thread;                                      // + weight_group_offset<0>(g)
+        float4* pb = reinterpret_cast<float4*>(o) + kLGroupsA * kLGroupThreads + ob.thread;         // + weight_group_offset<1>(g)
 #pragma unroll
         for (int q = 0; q < 6; ++q)
-            pa[q * kLThreads] = make_float4(logit[16 + 4 * q] * rz, logit[17 + 4 * q] * rz, logit[18 + 4 * q] * rz, logit[19 + 4 * q] * rz);
+            pa[(oa.slot * 6 + q) * kLGroupThreads] =
+                make_float4(logit[16 + 4 * q] * rz, logit[17 + 4 * q] * rz, logit[18 + 4 * q] * rz, logit[19 + 4 * q] * rz);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            pb[q * kLThreads] = make_float4(logit[4 * q] * rz, logit[4 * q + 1] * rz, logit[4 * q + 2] * rz, logit[4 * q + 3] * rz);
+            pb[(ob.slot * 4 + q) * kLGroupThreads] = make_float4(logit[4 * q] * rz, logit[4 * q + 1] * rz, logit[4 * q + 2] * rz, logit[4 * q + 3] * rz);
         if (D == 6) {
 #pragma unroll
             for (int q = 0; q < 2; ++q)
-                pb[(4 + q) * kLThreads] = make_float4(logit[P - 8 + 4 * q] * rz, logit[P - 7 + 4 * q] * rz, logit[P - 6 + 4 * q] * rz,
-                                                      logit[P - 5 + 4 * q] * rz);
+                pb[(kLGroupsBNear + ob.slot * 2 + q) * kLGroupThreads] =
+                    make_float4(logit[P - 8 + 4 * q] * rz, logit[P - 7 + 4 * q] * rz, logit[P - 6 + 4 * q] * rz, logit[P - 5 + 4 * q] * rz);
         }
     }
 }

@@ -115,7 +115,7 @@ def test_pamr_small_map_paths_agree(cl4, oracle, monkeypatch, path, B, C, H, W, 
     np.testing.assert_allclose(got, oracle.pamr(x, m, T, dil), rtol=RTOL, atol=ATOL)
 
 
-@pytest.mark.parametrize("mode", ["lattice", "nolattice"])
+@pytest.mark.parametrize("mode", ["lattice", "lattice1", "nolattice"])
 @pytest.mark.parametrize("B,C,H,W,T", [
     (2, 21, 96, 80, 10),     # partial tiles in x, 3 x 3 tiles
     (2, 3, 50, 72, 10),      # partial tiles in both dimensions
@@ -123,11 +123,13 @@ def test_pamr_small_map_paths_agree(cl4, oracle, monkeypatch, path, B, C, H, W, 
     (3, 2, 68, 132, 4),      # more tiles than one wave of classes; staggered class phase
     (1, 1, 72, 68, 1),       # single class, single iteration: straight to the output
     (5, 30, 160, 160, 2),    # 125 tiles x 30 classes: every CTA switches tiles (weight reload on the fly)
+    (2, 4, 36, 40, 3),       # even class count, 2 x 2 partial tiles
 ])
 @pytest.mark.parametrize("dil", [[1, 2, 4, 8, 12, 24], [1, 2, 4, 8, 12]])
 def test_pamr_lattice_sweep(cl4, oracle, monkeypatch, mode, dil, B, C, H, W, T):
-    """The two-group lattice sweep (pamr_lattice.cu) and the 4-pixel TMA sweep on the class-default dilation set
-    (wss/modules.py:125) and on the trainer's (train.py:81), each against the oracle."""
+    """The class-pair lattice sweep (pamr_duo.cu, the default: "lattice"), the one-class lattice sweep (pamr_lattice.cu,
+    "lattice1") and the 4-pixel TMA sweep on the class-default dilation set (wss/modules.py:125) and on the trainer's
+    (train.py:81), each against the oracle.  Odd and even class counts: an odd count runs one dummy class."""
     monkeypatch.setenv("CL4_SWEEP", mode)
     rng = np.random.default_rng(B * 1000 + C * 100 + H + W)
     x = (rng.integers(0, 256, (B, 3, H, W)) / 255.0).astype(np.float32)
@@ -201,6 +203,23 @@ def test_pamr_full_size_tile_vs_oracle(cl4, oracle):
     m = torch.from_numpy(rng.standard_normal((1, 3, 512, 512)).astype(np.float32)).softmax(1).numpy()
     want = oracle.pamr(x, m, 10, [1, 2, 4, 8, 12, 24])
     got = cl4.PAMR().cuda()(cuda(x), cuda(m)).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("B,C,H,W,dil", [
+    (1, 21, 512, 512, [1, 2, 4, 8, 12, 24]),   # the headline shape's class count on a full-size map (config 2)
+    (1, 81, 512, 512, [1, 2, 4, 8, 12, 24]),   # config 3 (COCO-to-VOC): 41 class pairs per tile
+    (1, 81, 512, 512, [1, 2, 4, 8, 12]),       # the trainer's dilation set at the same shape
+    (1, 3, 1024, 1024, [1, 2, 4, 8, 12, 24]),  # config 4 resolution: 1024 tiles, 7 tiles per CTA
+])
+def test_pamr_large_shapes_vs_oracle(cl4, oracle, B, C, H, W, dil):
+    """The class-pair sweep where it is benchmarked: the staggered pair phase (s0 = blockIdx * Cp / grid) and the
+    weight refill at tile switches depend on C and on the number of tiles per CTA (wss/modules.py:147-149)."""
+    rng = np.random.default_rng(C * 7 + H)
+    x = (rng.integers(0, 256, (B, 3, H, W)) / 255.0).astype(np.float32)
+    m = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).softmax(1).numpy()
+    want = oracle.pamr(x, m, 10, dil)
+    got = cl4.PAMR(10, dil).cuda()(cuda(x), cuda(m)).cpu().numpy()
     np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
 
 
