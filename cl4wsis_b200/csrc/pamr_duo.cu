@@ -30,9 +30,6 @@
 
 namespace cl4 {
 
-#ifndef CL4_DUO_DBG
-#define CL4_DUO_DBG 0
-#endif
 #ifndef CL4_DUO_STAGES
 #define CL4_DUO_STAGES 3
 #endif
@@ -42,9 +39,6 @@ namespace cl4 {
 
 typedef unsigned long long u64;
 
-#if CL4_DUO_DBG >= 8
-__device__ unsigned long long g_duo_dbg[16];  // [0] installs checked, [1] mismatching chunks right after the install, [2] before the first use
-#endif
 
 #ifdef CL4_DUO_FAKEW  // ablation (wrong results): only CL4_DUO_FAKEW weight registers are live -- what would free registers buy?
 #define CL4_DUO_WIDX(k) ((k) % CL4_DUO_FAKEW)
@@ -68,8 +62,11 @@ constexpr int kDPartCells = kTile * kDPartPitch;   // 1152 cells
 #define CL4_DUO_TMEM 1  // group B's dilation-{1,2} weights live in tensor memory (0: in registers, as pamr_lattice.cu)
 #endif
 constexpr bool kDTmem = CL4_DUO_TMEM != 0;
-constexpr int kDNearCols = 128;                    // TMEM columns per tile: row i * 32 + dilation h * 16 + column j * 8 + tap
-constexpr int kDTmemCols = 2 * kDNearCols;         // current tile + the tile visited next
+constexpr int kDNearCols = 128;                    // TMEM columns of the near weights: row i * 32 + dilation h * 16 + column j * 8 + tap
+constexpr int kDFarCols = 64;                      // ... of the dilation-24 weights: row i * 16 + column j * 8 + tap
+constexpr int kDTileCols = 256;                    // columns per tile (192 used); two tiles: the current one and the one visited next
+constexpr int kDTmemCols = 2 * kDTileCols;
+constexpr int kDBatches = 6;                       // installation batches of 8 float4 groups per tile: 4 near + 2 far
 constexpr size_t kDSmem = (size_t)kDStages * kDStageBytes + (size_t)kDParts * kDPartCells * 8 + (3 * kDStages + 8 * kDParts + 1) * 8 + 64;
 static_assert(kDSmem <= 227 * 1024, "duo sweep: shared memory");
 
@@ -185,13 +182,10 @@ __device__ __forceinline__ void duo_b_near(float (&w)[kLW], u64 (&acc)[kLPx], co
 // [pixel j = 0: taps 0..7][j = 1: taps 0..7]; the next chunk is in flight while this one computes.  A tcgen05.wait::ld keeps
 // later shared-memory loads below it, so the source rows are loaded explicitly ahead of the waits: rows i-2 .. i+2 of the
 // window are resident (six row slots of three LDS.128), row i+3 is fetched at the start of row i.
-__device__ __forceinline__ void duo_b_near_tmem(u64 (&acc)[kLPx], const u64* __restrict__ sp, const uint32_t tnear,
-                                                const float4* __restrict__ cw = nullptr) {
+__device__ __forceinline__ void duo_b_near_tmem(u64 (&acc)[kLPx], const u64* __restrict__ sp, const uint32_t tnear) {
     float wf[2][16];
     ulonglong2 row[6][3];
-#if CL4_DUO_DBG != 12
     tmem_ld16(wf[0], tnear);
-#endif
 #pragma unroll
     for (int r = -2; r <= 2; ++r)
 #pragma unroll
@@ -206,32 +200,8 @@ __device__ __forceinline__ void duo_b_near_tmem(u64 (&acc)[kLPx], const u64* __r
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int c = 2 * i + h, s = h + 1;
-#if CL4_DUO_DBG == 12   // no overlap: the chunk is loaded and waited for right here
-            tmem_ld16(wf[c & 1], tnear + 16 * c);
             tmem_wait_ld(wf[c & 1]);
-#else
-            tmem_wait_ld(wf[c & 1]);
-#if CL4_DUO_DBG == 10
-            tmem_wait_ld(wf[c & 1]);
-#endif
-#if CL4_DUO_DBG == 11
-            __syncwarp();
-#endif
             if (c + 1 < 8) tmem_ld16(wf[(c + 1) & 1], tnear + 16 * (c + 1));
-#endif
-#if CL4_DUO_DBG == 9
-            {   // do the registers hold what tensor memory holds?
-                const int b = c >> 1;
-                const float4 e0 = __ldcv(cw + (8 * b + 2 * h) * kLGroupThreads), e1 = __ldcv(cw + (8 * b + 2 * h + 1) * kLGroupThreads);
-                const float4 e2 = __ldcv(cw + (8 * b + 4 + 2 * h) * kLGroupThreads), e3 = __ldcv(cw + (8 * b + 5 + 2 * h) * kLGroupThreads);
-                const float ex[16] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
-                unsigned bad = 0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) bad += (wf[c & 1][j] != ex[j]);
-                if (bad) atomicAdd(&g_duo_dbg[c], 1ull);
-                atomicAdd(&g_duo_dbg[8 + c], 1ull);
-            }
-#endif
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 const int dy = (t < 3) ? -1 : ((t < 5) ? 0 : 1);
@@ -246,18 +216,50 @@ __device__ __forceinline__ void duo_b_near_tmem(u64 (&acc)[kLPx], const u64* __r
         }
     }
 }
-// eight float4 groups (slots 2b and 2b+1 of the near region, four groups each) -> the two chunks (b, 0), (b, 1)
-__device__ __forceinline__ void near_install(const float4 (&g)[8], const int b, const uint32_t tnear) {
-    tmem_st16(tnear + 32 * b, g[0], g[1], g[4], g[5]);
-    tmem_st16(tnear + 32 * b + 16, g[2], g[3], g[6], g[7]);
-}
-__device__ __forceinline__ void near_fetch(float4 (&g)[8], const float4* __restrict__ wp, const int b) {
+// Dilation 24 with the weights streamed from tensor memory: chunk i = pixel row i of the block, 16 columns
+// [pixel j = 0: taps 0..7][j = 1: taps 0..7].  The eight LDS.128 of a row are issued two rows ahead of their use (a
+// tcgen05.wait::ld keeps later shared-memory loads below it, so the loads are placed explicitly).
+__device__ __forceinline__ void duo_b_far_tmem(u64 (&acc)[kLPx], const u64* __restrict__ sp, const uint32_t tfar) {
+    float wf[2][16];
+    ulonglong2 src[3][8];
+    tmem_ld16(wf[0], tfar);
+    auto load_row = [&](ulonglong2 (&d)[8], const int i) {
 #pragma unroll
-#if CL4_DUO_DBG == 5
-    for (int n = 0; n < 8; ++n) g[n] = __ldcv(wp + (8 * b + n) * kLGroupThreads);
-#else
-    for (int n = 0; n < 8; ++n) g[n] = __ldg(wp + (8 * b + n) * kLGroupThreads);  // near region: group slot*4 + q at [group][thread]
-#endif
+        for (int a = -1; a <= 1; ++a)
+#pragma unroll
+            for (int b = -1; b <= 1; ++b)
+                if (a != 0 || b != 0) d[tap_index(a, b)] = *reinterpret_cast<const ulonglong2*>(sp + (i + 24 * a) * kDPitch + 24 * b);
+    };
+    load_row(src[0], 0);
+    load_row(src[1], 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i + 2 < 4) load_row(src[(i + 2) % 3], i + 2);
+        tmem_wait_ld(wf[i & 1]);
+        if (i + 1 < 4) tmem_ld16(wf[(i + 1) & 1], tfar + 16 * (i + 1));
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            ffma2(acc[i * 2], src[i % 3][t].x, wf[i & 1][t]);
+            ffma2(acc[i * 2 + 1], src[i % 3][t].y, wf[i & 1][8 + t]);
+        }
+    }
+}
+// Installation of a tile's weights in tensor memory, in batches of eight float4 groups (32 registers in flight):
+// batch b < 4: near groups 8b .. 8b+7 (slots 2b and 2b+1, four groups each) -> the chunks (b, 0), (b, 1);
+// batch 4, 5:  far groups 8(b-4) .. +7 (slots 4(b-4) .. +3, two groups each) -> the far chunks 2(b-4), 2(b-4)+1.
+// wp: the thread's base pointer into the tile's weight block (group B: its near region; the far region follows it).
+__device__ __forceinline__ void tile_fetch(float4 (&g)[8], const float4* __restrict__ wp, const int b) {
+#pragma unroll
+    for (int n = 0; n < 8; ++n) g[n] = __ldg(wp + (8 * b + n) * kLGroupThreads);  // near groups 0..31, then far groups 32..47
+}
+__device__ __forceinline__ void tile_install(const float4 (&g)[8], const int b, const uint32_t tt) {
+    if (b < 4) {
+        tmem_st16(tt + 32 * b, g[0], g[1], g[4], g[5]);
+        tmem_st16(tt + 32 * b + 16, g[2], g[3], g[6], g[7]);
+    } else {
+        tmem_st16(tt + kDNearCols + 32 * (b - 4), g[0], g[1], g[2], g[3]);
+        tmem_st16(tt + kDNearCols + 32 * (b - 4) + 16, g[4], g[5], g[6], g[7]);
+    }
 }
 
 struct DuoOut {
@@ -404,23 +406,19 @@ __device__ __forceinline__ void duo_group(const DuoCtx& cx, const DuoOut& out) {
     const float4* const wbase = reinterpret_cast<const float4*>(cx.wts) + weight_thread_base(tid);
     auto weight_ptr = [&](int tile) -> const float4* { return wbase + (size_t)tile * (kLWeightsPerTile / 4); };
 
-    float w[kLW];
+    float w[kLW];  // (group B with its weights in tensor memory never touches it)
     u64 acc[kLPx];
-    // group B, near weights in tensor memory: this warp's lane quadrant, columns [0,128) and [128,256) alternate between visits
-    uint32_t tnear = cx.tmem_base + ((uint32_t)((tid >> 5) & 3) << 21), tnext = tnear + kDNearCols;
+    // group B, weights in tensor memory: this warp's lane quadrant, columns [0,256) and [256,512) alternate between visits
+    uint32_t tcur = cx.tmem_base + ((uint32_t)((tid >> 5) & 3) << 21), tnext = tcur + kDTileCols;
 
     int tile = blockIdx.x, q = cx.s0, left = cx.total;
     if (left > 0) {
         if (kT) {
-            // far weights (groups slot*6 + 4, 5) into registers; near weights into tensor memory
-#pragma unroll
-            for (int g = 0; g < kLW / 4; ++g)
-                if ((g % 6) >= 4) load_weight_group<1>(w, weight_ptr(tile), g);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
+#pragma unroll 1
+            for (int b = 0; b < kDBatches; ++b) {
                 float4 g8[8];
-                near_fetch(g8, weight_ptr(tile), b);
-                near_install(g8, b, tnear);
+                tile_fetch(g8, weight_ptr(tile), b);
+                tile_install(g8, b, tcur);
             }
             tmem_wait_st();
         } else {
@@ -436,7 +434,7 @@ __device__ __forceinline__ void duo_group(const DuoCtx& cx, const DuoOut& out) {
         const int n_q = min(cx.Cp - q, left);
         int next_tile = tile + (int)gridDim.x;
         if (next_tile >= cx.n_tiles) next_tile = blockIdx.x;
-        const bool switch_tile = (left > n_q) && (next_tile != tile);  // another tile follows: refill the weights on the fly
+        const bool switch_tile = (left > n_q) && (next_tile != tile);  // another tile follows: its weights are fetched during this visit
         const float4* const nw = weight_ptr(next_tile);
         if (switch_tile && (lane & 7) == 0) {
             // the next visit's weights into L2 a whole visit ahead: four 128-byte lines per warp and float4 group
@@ -468,32 +466,14 @@ __device__ __forceinline__ void duo_group(const DuoCtx& cx, const DuoOut& out) {
                 if (reload) duo_a<true>(w, acc, sp, nw);
                 else duo_a<false>(w, acc, sp, nw);
             } else if (kT) {
-                // dilation 24 first (weights in registers, every load in flight), then the near taps from tensor memory.  One
-                // batch of the next visit's near weights is fetched before and installed after the dilation-24 part, which
-                // has the registers to spare
-#if CL4_DUO_DBG >= 3
-                const bool do_batch = false;  // (debug variants)
-#else
-                const bool do_batch = switch_tile && e < 4;
-#endif
+                // One batch of the next visit's weights per item: fetched before the dilation-24 part (which has registers to
+                // spare while the loads are in flight) and installed in the other half of the columns after it.
+                const bool do_batch = switch_tile && e < kDBatches;
                 float4 g8[8];
-                if (do_batch) near_fetch(g8, nw, e);
-                if (reload) duo_b_far<true>(w, acc, sp, nw);
-                else duo_b_far<false>(w, acc, sp, nw);
-#if CL4_DUO_DBG == 2
-                duo_b_near_tmem(acc, sp, tnear);
-                if (do_batch) near_install(g8, e, tnext);
-#elif CL4_DUO_DBG == 9
-                duo_b_near_tmem(acc, sp, tnear, weight_ptr(tile));
-#else
-                if (do_batch) {
-                    near_install(g8, e, tnext);
-#if CL4_DUO_DBG == 1
-                    tmem_wait_st();
-#endif
-                }
-                duo_b_near_tmem(acc, sp, tnear);
-#endif
+                if (do_batch) tile_fetch(g8, nw, e);
+                duo_b_far_tmem(acc, sp, tcur + kDNearCols);
+                if (do_batch) tile_install(g8, e, tnext);
+                duo_b_near_tmem(acc, sp, tcur);
             } else {
                 if (kFar) {
                     if (reload) duo_b_far<true>(w, acc, sp, nw);
@@ -553,8 +533,6 @@ __device__ __forceinline__ void duo_group(const DuoCtx& cx, const DuoOut& out) {
                     }
                     oc += 2 * out.plane;
                 }
-            }
-            if (G == 1) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive_u32(empty0 + 8u * stage);  // after the global stores (see group A above)
             }
@@ -565,64 +543,16 @@ __device__ __forceinline__ void duo_group(const DuoCtx& cx, const DuoOut& out) {
             }
         }
 
-#if CL4_DUO_DBG == 8
-        if (kT) {  // is the current half still what was installed?
-            unsigned bad = 0;
-            const float4* cw = weight_ptr(tile);
-            for (int c = 0; c < 8; ++c) {
-                float rb[16];
-                tmem_ld16(rb, tnear + 16 * c);
-                tmem_wait_ld(rb);
-                const int b = c >> 1, h = c & 1;
-                const float4 e0 = __ldcv(cw + (8 * b + 2 * h) * kLGroupThreads), e1 = __ldcv(cw + (8 * b + 2 * h + 1) * kLGroupThreads);
-                const float4 e2 = __ldcv(cw + (8 * b + 4 + 2 * h) * kLGroupThreads), e3 = __ldcv(cw + (8 * b + 5 + 2 * h) * kLGroupThreads);
-                const float ex[16] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
-                for (int j = 0; j < 16; ++j) bad += (rb[j] != ex[j]);
-            }
-            if (bad) atomicAdd(&g_duo_dbg[2], 1ull);
-            atomicAdd(&g_duo_dbg[3], 1ull);
-        }
-#endif
-        if (kT && switch_tile) {  // finish the installation of the next visit's near weights (visits shorter than four items)
-#if CL4_DUO_DBG == 4
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-#endif
-#if CL4_DUO_DBG == 6
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#endif
-            for (int b = (CL4_DUO_DBG >= 3 ? 0 : n_q); b < 4; ++b) {
+        if (kT && switch_tile) {  // finish the installation of the next visit's weights (visits shorter than six items), switch halves
+#pragma unroll 1
+            for (int b = n_q; b < kDBatches; ++b) {
                 float4 g8[8];
-                near_fetch(g8, nw, b);
-                near_install(g8, b, tnext);
+                tile_fetch(g8, nw, b);
+                tile_install(g8, b, tnext);
             }
             tmem_wait_st();
-#if CL4_DUO_DBG == 4
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-#endif
-#if CL4_DUO_DBG == 7
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#endif
-#if CL4_DUO_DBG == 8
-            {   // read the installed columns back and compare with the global copy
-                unsigned bad = 0;
-                for (int c = 0; c < 8; ++c) {
-                    float rb[16];
-                    tmem_ld16(rb, tnext + 16 * c);
-                    tmem_wait_ld(rb);
-                    const int b = c >> 1, h = c & 1;
-                    const float4 e0 = __ldcv(nw + (8 * b + 2 * h) * kLGroupThreads), e1 = __ldcv(nw + (8 * b + 2 * h + 1) * kLGroupThreads);
-                    const float4 e2 = __ldcv(nw + (8 * b + 4 + 2 * h) * kLGroupThreads), e3 = __ldcv(nw + (8 * b + 5 + 2 * h) * kLGroupThreads);
-                    const float ex[16] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
-                    for (int j = 0; j < 16; ++j) bad += (rb[j] != ex[j]);
-                }
-                atomicAdd(&g_duo_dbg[0], 1ull);
-                if (bad) atomicAdd(&g_duo_dbg[1], 1ull);
-            }
-#endif
-            const uint32_t t = tnear;
-            tnear = tnext;
+            const uint32_t t = tcur;
+            tcur = tnext;
             tnext = t;
         }
         left -= n_q;
@@ -765,9 +695,3 @@ int launch_sweep_duo(const float* w, const float* cells_in, float* out, int out_
 }
 
 }  // namespace cl4
-
-#if CL4_DUO_DBG >= 8
-extern "C" int cl4_debug_duo(unsigned long long* out4) {
-    return (int)cudaMemcpyFromSymbol(out4, cl4::g_duo_dbg, sizeof(unsigned long long) * 16);
-}
-#endif
