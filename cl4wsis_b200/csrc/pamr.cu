@@ -359,14 +359,15 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
         rc = dispatch_D<WeightsLauncher>(D, img, wts, B, K, H, W, dil, use_tma ? 1 : 0, s);
     }
     if (rc != CL4_OK) return rc;
-    if (use_lattice && !force_lat1) {
-        // class-pair sweep: pack the planar masks into pair cells, ping-pong A -> B -> A ..., the last sweep writes planar
+    if (use_lattice && !force_lat1 && num_iter >= 2) {
+        // class-pair sweeps.  The first sweep is the one-class lattice kernel reading the caller's planar masks and writing
+        // pair cells (a separate pack pass would read and write every mask once more); the last one writes planar.
         if ((rc = record(ev_sweeps_begin)) != CL4_OK) return rc;
-        rc = launch_duo_pack(mask_in, bufA, B, C, H, W, s);
+        rc = launch_sweep_lattice(wts, mask_in, W, (long long)H * W, bufA, duo_pitch(W), (long long)duo_plane_elems(H, W), 1, B, C, H, W, D, s);
         if (rc != CL4_OK) return rc;
         float* cur = bufA;
         float* nxt = bufB;
-        for (int it = 0; it < num_iter; ++it) {
+        for (int it = 1; it < num_iter; ++it) {
             const bool last = (it == num_iter - 1);
             rc = launch_sweep_duo(wts, cur, last ? mask_out : nxt, last ? 1 : 0, B, C, H, W, D, s);
             if (rc != CL4_OK) return rc;
@@ -388,7 +389,7 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
         for (int it = 0; it < num_iter; ++it) {
             const bool last = (it == num_iter - 1);
             float* dst = last ? mask_out : nxt;
-            rc = launch_sweep_lattice(wts, cur, cur_pitch, cur_plane, dst, last ? W : sp, last ? (long long)H * W : splane, B, C, H, W, D, s);
+            rc = launch_sweep_lattice(wts, cur, cur_pitch, cur_plane, dst, last ? W : sp, last ? (long long)H * W : splane, 0, B, C, H, W, D, s);
             if (rc != CL4_OK) return rc;
             cur = dst;
             cur_pitch = sp;

@@ -24,8 +24,8 @@
 //     half while the current tile computes, so a tile switch costs nothing.
 // An odd class count costs one dummy class (C = 21: +4.8 % work); its cells are zero and stay zero.
 //
-// The first sweep reads cells packed from the caller's planar masks by pamr_duo_pack_kernel; the last sweep writes the
-// planar [B,C,H,W] result directly.
+// The first sweep of a PAMR call is the one-class kernel of pamr_lattice.cu reading the caller's planar masks and writing
+// cells; the last sweep writes the planar [B,C,H,W] result directly.
 #include "pamr_lattice.cuh"
 
 namespace cl4 {
@@ -632,37 +632,10 @@ pamr_sweep_duo_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
     }
 }
 
-// Planar masks [B][C][H][W] -> pair cells [B][Cp][H][pitch/2][2] (the first sweep's input).  One thread per 4 pixels of a
-// row of one pair plane; a missing second class (odd C) becomes zeros, which every sweep maps to zeros again.
-__global__ void __launch_bounds__(256)
-pamr_duo_pack_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int Cp, int H, int W, int pitch, long long plane) {
-    const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    const int bq = blockIdx.z;
-    if (x4 * 4 >= W) return;
-    const int b = bq / Cp, q = bq - b * Cp;
-    const size_t HW = (size_t)H * W;
-    const float* p0 = in + ((size_t)b * C + 2 * q) * HW + (size_t)y * W + 4 * x4;
-    const float4 a = __ldcs(reinterpret_cast<const float4*>(p0));
-    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (2 * q + 1 < C) c = __ldcs(reinterpret_cast<const float4*>(p0 + HW));
-    float4* o = reinterpret_cast<float4*>(out + (size_t)bq * plane + (size_t)y * pitch + 8 * x4);
-    o[0] = make_float4(a.x, c.x, a.y, c.y);
-    o[1] = make_float4(a.z, c.z, a.w, c.w);
-}
-
 // ------------------------------------------------------------------------------------------ host
 int duo_pitch(int W) { return 2 * (W + 2 * kPamrPad); }  // floats per row of a pair plane (never a power of two, see pamr.cu)
 size_t duo_plane_elems(int H, int W) { return (size_t)H * duo_pitch(W); }
 size_t duo_buffer_elems(int B, int C, int H, int W) { return (size_t)B * ((C + 1) / 2) * duo_plane_elems(H, W); }
-
-int launch_duo_pack(const float* mask_in, float* cells, int B, int C, int H, int W, cudaStream_t s) {
-    const int Cp = (C + 1) / 2;
-    CL4_REQUIRE((long long)B * Cp <= 65535 && H <= 65535, CL4_EUNSUPPORTED, "pamr_duo_pack: B*ceil(C/2) or H > 65535");
-    dim3 grid(ceil_div(W / 4, 128), H, B * Cp);
-    pamr_duo_pack_kernel<<<grid, 128, 0, s>>>(mask_in, cells, C, Cp, H, W, duo_pitch(W), (long long)duo_plane_elems(H, W));
-    return check_launch("pamr_duo_pack");
-}
 
 // cells_in: pair cells (duo_buffer_elems).  out_planar == 0: `out` is another pair-cell buffer; otherwise the caller's
 // planar [B,C,H,W] tensor.

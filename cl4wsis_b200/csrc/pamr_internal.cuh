@@ -30,14 +30,16 @@ size_t lattice_weight_elems(int B, int H, int W);
 int launch_weights_lattice(const float* padded_img, float* w, int B, int K, int H, int W, int D, cudaStream_t s);
 // in / out: planes of H x W pixels, rows `pitch` and planes `plane` elements apart (the replicate padding happens
 // inside the kernel's shared-memory ring; nothing around the image area is read or written)
+// out_cells != 0: `out` is a pair-cell buffer (duo_buffer_elems; pitch = duo_pitch, plane = pair plane), the layout the
+// class-pair sweep reads
 int launch_sweep_lattice(const float* w, const float* in, int in_pitch, long long in_plane, float* out, int out_pitch,
-                         long long out_plane, int B, int C, int H, int W, int D, cudaStream_t s);
+                         long long out_plane, int out_cells, int B, int C, int H, int W, int D, cudaStream_t s);
 
 // Class-pair ("duo") sweep for the same two dilation sets (pamr_duo.cu): the masks between sweeps are pair-interleaved cells
 // [B][ceil(C/2)][H][W + 48][2]; packed fp32 FMAs on both classes of a cell.  Weights: the lattice layout.
 int duo_pitch(int W);                                          // floats per row of a pair plane
+size_t duo_plane_elems(int H, int W);                          // floats per pair plane
 size_t duo_buffer_elems(int B, int C, int H, int W);           // floats per pair-cell buffer
-int launch_duo_pack(const float* mask_in, float* cells, int B, int C, int H, int W, cudaStream_t s);  // planar -> cells
 int launch_sweep_duo(const float* w, const float* cells_in, float* out, int out_planar, int B, int C, int H, int W, int D,
                      cudaStream_t s);
 

@@ -262,7 +262,8 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
         const LTile tc = ltile(blockIdx.x + kk * gridDim.x, cx.tiles_x, cx.tiles_per_img);
         const int y = tc.y0 + ry, x = tc.x0 + rx;
         nrows = (x < cx.W) ? min(max(cx.H - y, 0), 4) : 0;
-        o = out.ptr + (long long)tc.b * C * out.plane + (long long)y * out.pitch + x;
+        o = out.cells ? out.ptr + (long long)tc.b * ((C + 1) >> 1) * out.plane + (long long)y * out.pitch + 2 * x
+                      : out.ptr + (long long)tc.b * C * out.plane + (long long)y * out.pitch + x;
     };
     if (cx.total > 0) {
         enter_tile(0);
@@ -277,7 +278,9 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
     uint32_t full_phase = 0, part_phase = 0;
     const float* sp = cx.stage0 + tb;
     float* pp = cx.part + pbase;
-    float* oc = (G == 1) ? o + (long long)c * out.plane : nullptr;
+    // planes: class c at o + c * plane; cells: class c is half (c & 1) of pair plane c >> 1
+    auto class_ptr = [&](int cc) -> float* { return out.cells ? o + (long long)(cc >> 1) * out.plane + (cc & 1) : o + (long long)cc * out.plane; };
+    float* oc = (G == 1) ? class_ptr(c) : nullptr;
 
     for (int item = 0; item < cx.total; ++item) {
         // last class of this tile visit and another tile follows: refill the weights on the fly
@@ -323,15 +326,28 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
             for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float2*>(pp + i * kLPartPitch);
             __syncwarp();
             if (lane == 0) mbar_arrive_u32(pempty0 + 32u * pb);
+            // the output is not read again before the next sweep: evict-first stores keep L2 for windows and weights
+            if (!out.cells) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                // the output is not read again before the next sweep: evict-first stores keep L2 for windows and weights
-                if (i < nrows)
-                    __stcs(reinterpret_cast<float2*>(oc + (long long)i * out.pitch), make_float2(acc[2 * i] + a[i].x, acc[2 * i + 1] + a[i].y));
+                for (int i = 0; i < 4; ++i)
+                    if (i < nrows)
+                        __stcs(reinterpret_cast<float2*>(oc + (long long)i * out.pitch), make_float2(acc[2 * i] + a[i].x, acc[2 * i + 1] + a[i].y));
+            } else if ((C & 1) && c == C - 1) {
+                // odd class count: the last class shares its cells with a dummy class that has to be zero
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < nrows)
+                        __stcs(reinterpret_cast<float4*>(oc + (long long)i * out.pitch), make_float4(acc[2 * i] + a[i].x, 0.f, acc[2 * i + 1] + a[i].y, 0.f));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < nrows) {
+                        __stcs(oc + (long long)i * out.pitch, acc[2 * i] + a[i].x);
+                        __stcs(oc + (long long)i * out.pitch + 2, acc[2 * i + 1] + a[i].y);
+                    }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive_u32(empty0 + 8u * stage);  // this warp no longer reads the window
-            oc += out.plane;
         }
 
         sp += kLStageFloats;
@@ -352,8 +368,8 @@ __device__ __forceinline__ void lattice_group(const LatticeCtx& cx, const Lattic
                 k = nk;
                 enter_tile(k);
             }
-            if (G == 1) oc = o;
         }
+        if (G == 1) oc = class_ptr(c);
     }
 }
 
@@ -545,7 +561,7 @@ int launch_weights_lattice(const float* padded_img, float* w, int B, int K, int 
 }
 
 int launch_sweep_lattice(const float* w, const float* in, int in_pitch, long long in_plane, float* out, int out_pitch,
-                         long long out_plane, int B, int C, int H, int W, int D, cudaStream_t s) {
+                         long long out_plane, int out_cells, int B, int C, int H, int W, int D, cudaStream_t s) {
     CUtensorMap tmap;  // over the H x W image area of each plane; boxes may start at negative coordinates (zero fill)
     const int rc = encode_tmap_3d_f32_strided(&tmap, in, W, H, (long long)B * C, in_pitch, in_plane, kLPitch, kBox);
     if (rc != 0) {
@@ -556,6 +572,7 @@ int launch_sweep_lattice(const float* w, const float* in, int in_pitch, long lon
     so.ptr = out;
     so.plane = out_plane;
     so.pitch = out_pitch;
+    so.cells = out_cells ? 1 : 0;
     const int tiles_x = ceil_div(W, kTile), tiles_y = ceil_div(H, kTile);
     const int n_tiles = B * tiles_x * tiles_y;
     auto kern = D == 6 ? pamr_sweep_lattice_kernel<true> : pamr_sweep_lattice_kernel<false>;
@@ -582,4 +599,3 @@ extern "C" int cl4_lattice_owner(int group, int y, int x, int* thread_out, int* 
     *slot_out = o.slot;
     return CL4_OK;
 }
-

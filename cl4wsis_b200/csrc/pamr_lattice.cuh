@@ -104,8 +104,9 @@ __device__ __forceinline__ void load_weights(float (&w)[kLW], const float4* __re
 
 struct LatticeOut {
     float* ptr;       // element (plane 0, y = 0, x = 0) of the output
-    long long plane;  // elements between planes
+    long long plane;  // elements between planes (cells: between pair planes)
     int pitch;        // elements between rows (even)
+    int cells;        // 0: planes [B*C][H][W]; 1: pair-interleaved cells [B*ceil(C/2)][H][pitch/2][2] (what pamr_duo.cu reads)
 };
 
 struct LTile {

@@ -36,16 +36,17 @@ class PseudoLabelStep:
         self.ids = torch.empty((B, H, W), dtype=torch.int64, device=dev)
         self.centers = torch.zeros((B, self.max_centers, 2), dtype=torch.int64, device=dev)
         self.counts = torch.zeros((B,), dtype=torch.int32, device=dev)
-        # launches per step.  Class-pair lattice sweep (class-default dilations, the replicate padding happens inside the
-        # kernel): image pad, weights, mask pack, num_iter sweeps, 2 NMS, grouping.  One-class lattice sweep (CL4_SWEEP=lattice1):
-        # no pack.  4-pixel TMA sweep: image pad, weights, mask pad, num_iter sweeps, num_iter-1 frame rewrites, 2 NMS, grouping.
+        # launches per step.  Lattice sweeps (class-default dilations, the replicate padding happens inside the kernels): image
+        # pad, weights, num_iter sweeps (the first one the one-class kernel writing pair cells, the others the class-pair
+        # kernel; CL4_SWEEP=lattice1: the one-class kernel throughout), 2 NMS, grouping.  4-pixel TMA sweep: image pad, weights,
+        # mask pad, num_iter sweeps, num_iter-1 frame rewrites, 2 NMS, grouping.
         import os
         mode = os.environ.get("CL4_SWEEP")
         lattice = (self.dil in ([1, 2, 4, 8, 12, 24], [1, 2, 4, 8, 12]) and K <= 3 and W % 4 == 0 and H * W > 64 * 64
                    and mode in (None, "", "lattice", "lattice1"))
-        self.sweep_kernel = ("pamr_sweep_duo_kernel" if lattice and mode != "lattice1"
+        self.sweep_kernel = ("pamr_sweep_duo_kernel" if lattice and mode != "lattice1" and self.num_iter >= 2
                              else "pamr_sweep_lattice_kernel" if lattice else "pamr_sweep_tma_kernel")
-        self.launches_per_step = (1 + 1 + (0 if mode == "lattice1" else 1) + self.num_iter + 2 + 1 if lattice
+        self.launches_per_step = (1 + 1 + self.num_iter + 2 + 1 if lattice
                                   else 1 + 1 + 1 + self.num_iter + max(self.num_iter - 1, 0) + 2 + 1)
 
     def run(self, img, mask, heat, offsets, fg=None, stream=None, sweep_events=None):
