@@ -43,3 +43,40 @@ def reduce_stats(n_images, elapsed_s, checksum_mask, checksum_ids, device="cpu")
 def barrier():
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
+
+
+_AFFINITY_NOTE = "unchanged"
+
+
+def pin_to_local_cpus(local_rank):
+    """Bind this process to the CPU cores NVML reports as local to its GPU (the cores of the GPU's NUMA node), so that
+    the pinned host buffers of the end-to-end path are allocated from, and copied out of, node-local memory.  When
+    several ranks share the same core set (one NUMA node for all GPUs), each rank takes its own contiguous slice, which
+    keeps the ranks' submit threads from migrating over one another.  Best effort: returns a description, never raises."""
+    global _AFFINITY_NOTE
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cores = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            _AFFINITY_NOTE = "NVML affinity empty; unchanged"
+            return _AFFINITY_NOTE
+        world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+        if world > 1 and len(allowed) >= 2 * world:
+            per = len(allowed) // world
+            mine = allowed[local_rank * per:(local_rank + 1) * per]
+        else:
+            mine = allowed
+        os.sched_setaffinity(0, mine)
+        _AFFINITY_NOTE = f"cores {mine[0]}-{mine[-1]} ({len(mine)} of the {len(allowed)} NVML-local cores of GPU {local_rank})"
+    except Exception as e:  # noqa: BLE001
+        _AFFINITY_NOTE = f"unchanged ({type(e).__name__})"
+    return _AFFINITY_NOTE
+
+
+def affinity_note():
+    return _AFFINITY_NOTE

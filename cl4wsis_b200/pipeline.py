@@ -130,3 +130,29 @@ class HostPseudoLabelPipeline:
     def drain(self):
         for s in self.slots:
             s["ev_out"].synchronize()
+
+    def copy_floor(self, h_img, h_mask, h_heat, h_off, n=20):
+        """The floor of the end-to-end leg on this box: the copies of ``submit`` (inputs host -> device on one stream,
+        results device -> host on another, concurrently) with no kernels in between.  -> {"steps", "seconds"}."""
+        import time
+
+        def one(s):
+            with torch.cuda.stream(self.s_in):
+                s["img"].copy_(h_img, non_blocking=True)
+                s["mask"].copy_(h_mask, non_blocking=True)
+                s["heat"].copy_(h_heat, non_blocking=True)
+                s["off"].copy_(h_off, non_blocking=True)
+            with torch.cuda.stream(self.s_out):
+                s["h_refined"].copy_(s["step"].refined, non_blocking=True)
+                s["h_ids"].copy_(s["step"].ids, non_blocking=True)
+                s["h_counts"].copy_(s["step"].counts, non_blocking=True)
+
+        self.drain()
+        for i in range(2):
+            one(self.slots[i % len(self.slots)])
+        torch.cuda.synchronize(self.device)
+        t0 = time.perf_counter()
+        for i in range(n):
+            one(self.slots[i % len(self.slots)])
+        torch.cuda.synchronize(self.device)
+        return {"steps": n, "seconds": time.perf_counter() - t0}

@@ -1,7 +1,8 @@
 """CPU parity oracle for the CL4WSIS pseudo-label hot path (TEST INFRASTRUCTURE ONLY).
 
 Importable only from tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s
-``cpu_baseline`` / ``--impl reference`` legs.  The product package
+``cpu_baseline`` / ``--impl reference`` / ``torch_gpu_baseline`` legs (``oracle.torch_ref``: the same path restated
+with stock PyTorch ops, the second oracle that runs on CUDA tensors).  The product package
 ``cl4wsis_b200`` never imports this.
 """
 from .oracle import (  # noqa: F401

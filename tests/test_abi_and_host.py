@@ -144,6 +144,38 @@ def test_bench_reference_arm_prints_one_json_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # both arms print the SAME config object (the driver compares them key for key)
+    import bench
+    assert d["config"] == bench.bench_config("voc_b16_c21_512", bench.WORKLOADS["voc_b16_c21_512"])
+
+
+def test_bench_inputs_do_not_depend_on_sharding():
+    """Synthetic images are seeded by GLOBAL image index: rank r's batch is images r*B .. r*B+B-1 of the job."""
+    import bench
+    import torch
+    cfg = dict(B=4, C=3, H=32, W=32, dil=[1, 2], T=1, Kc=2, nms=5, thr=0.3)
+    whole = bench.synth_inputs(cfg, 0, 4)
+    for r in range(2):
+        part = bench.synth_inputs(cfg, 2 * r, 2)
+        for a, b in zip(part, whole):
+            assert torch.equal(a, b[2 * r:2 * r + 2])
+
+
+def test_traffic_lookup_refuses_stale_captures(tmp_path, monkeypatch):
+    """roofline.traffic is read from profiles/traffic.json only for a capture of THIS build of the sweep kernels."""
+    import json
+    import bench
+    sha = bench.sweep_sources_sha()
+    doc = {"entries": [
+        {"workload": "w1", "kernel": "k", "sources_sha": sha, "dram_bytes_read": 3.0, "dram_bytes_write": 4.0, "report": "a"},
+        {"workload": "w2", "kernel": "k", "sources_sha": "0" * 16, "dram_bytes_read": 3.0, "dram_bytes_write": 4.0, "report": "b"}]}
+    (tmp_path / "profiles").mkdir()
+    (tmp_path / "profiles" / "traffic.json").write_text(json.dumps(doc))
+    (tmp_path / "cl4wsis_b200").symlink_to(os.path.join(ROOT, "cl4wsis_b200"))
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench.measured_traffic("w1", "k")[0] == 7.0
+    assert bench.measured_traffic("w2", "k")[0] is None and "this build" in bench.measured_traffic("w2", "k")[1]
+    assert bench.measured_traffic("w3", "k")[0] is None
 
 
 def test_lattice_sweep_layout_invariants(lib):

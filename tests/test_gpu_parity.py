@@ -662,3 +662,108 @@ def test_phase1_error_behaviour(cl4):
         denorm(torch.zeros(2, 4, 8, 8, device="cuda"))           # utils/utils.py:35 "Expected RGB image"
     with pytest.raises(RuntimeError):
         denorm(torch.zeros(2, 3, 8, 8))                           # CPU tensor: no fallback
+
+
+# --------------------------------------------------------------------------- second oracle: stock PyTorch ON THE GPU
+@pytest.fixture()
+def fp32_convs():
+    """ATen's CUDA convolutions default to TF32 (torch.backends.cudnn.allow_tf32); the reference's one-hot shift kernels
+    would then see masks rounded to 10 mantissa bits.  The parity bar is fp32 arithmetic, so TF32 is off here."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("B,C,H,W,dil,T", [
+    (2, 21, 128, 160, [1, 2, 4, 8, 12, 24], 10),   # class-pair sweep, odd class count
+    (1, 4, 256, 256, [1, 2, 4, 8, 12], 10),        # the trainer's dilation set
+    (16, 21, 32, 32, [1, 2, 4, 8, 12], 10),        # the trainer's real regime (fused small-map kernel), train.py:376-379
+    (2, 3, 56, 56, [1, 2, 4, 8, 12], 10),
+])
+def test_pamr_vs_stock_pytorch_on_cuda(cl4, fp32_convs, B, C, H, W, dil, T):
+    """wss/modules.py:133-152 executed by ATen's CUDA kernels (F.pad + F.conv2d + std + softmax) on the same device."""
+    from oracle import torch_ref as tr
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + C)
+    x = (torch.randint(0, 256, (B, 3, H, W), generator=g).float() / 255).cuda()
+    m = torch.randn((B, C, H, W), generator=g).softmax(1).cuda()
+    want = tr.pamr(x, m, T, dil)
+    got = cl4.PAMR(T, dil).cuda()(x, m)
+    torch.testing.assert_close(got, want, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("H,W,Kc", [(512, 512, 5), (256, 320, 200), (64, 50, 1000), (1024, 1024, 50)])
+def test_group_pixels_vs_torch_norm_on_cuda(cl4, H, W, Kc):
+    """SURVEY §7.2 / ADVICE: the ids are pinned to ATen's CPU 2-vector norm, sqrt(fma(dx,dx,rn(dy^2))).  ATen's CUDA norm
+    kernel may round differently; the trainer runs group_pixels on CUDA (train.py:492 -> modules/utils.py:604).
+    Requirement: the ids equal torch.norm + argmin ON THIS DEVICE except where the two nearest centres are tied to
+    within 2 ulp of the distance (there the argmin depends on one rounding, and the CPU reference is the pin)."""
+    from oracle import torch_ref as tr
+    from cl4wsis_b200.modules import utils as mu
+    g = torch.Generator(device="cpu").manual_seed(H + Kc)
+    ctr = torch.stack([torch.randint(0, H, (Kc,), generator=g), torch.randint(0, W, (Kc,), generator=g)], 1).cuda()
+    off = (20 * torch.randn((1, 2, H, W), generator=g)).cuda()
+    got = mu.group_pixels(ctr, off)
+    want = tr.group_pixels(ctr.float(), off)
+    diff = got != want
+    n_bad = int(diff.sum())
+    if n_bad:
+        yy, xx = torch.nonzero(diff[0], as_tuple=True)
+        loc = torch.stack([yy.float() + off[0, 0, yy, xx], xx.float() + off[0, 1, yy, xx]], 1).double()
+        c = ctr.double()
+        d_got = (c[got[0, yy, xx] - 1] - loc).norm(dim=-1)
+        d_want = (c[want[0, yy, xx] - 1] - loc).norm(dim=-1)
+        rel = ((d_got - d_want).abs() / d_want.clamp_min(1e-30)).max().item()
+        assert rel <= 2.5e-7, f"{n_bad} ids differ from torch-CUDA and are not fp32 ties (rel distance gap {rel:.3e})"
+    assert n_bad <= max(4, H * W * Kc // 200000), f"{n_bad} tie-order differences vs torch-CUDA"
+
+
+@pytest.mark.parametrize("H,W,k,thr", [(512, 512, 41, 0.3), (100, 333, 3, 0.1), (65, 31, 7, 0.5)])
+def test_center_nms_vs_torch_maxpool_on_cuda(cl4, H, W, k, thr):
+    """modules/utils.py:478-492 on CUDA tensors: F.threshold + F.max_pool2d + nonzero -> identical centre list."""
+    from oracle import torch_ref as tr
+    from cl4wsis_b200.modules import utils as mu
+    g = torch.Generator(device="cpu").manual_seed(H * 3 + k)
+    heat = (torch.rand((1, 1, H, W), generator=g) * 64).round() / 64   # exact plateaus
+    heat = heat.cuda()
+    want = tr.find_instance_center(heat.clone(), thr, k)
+    got = mu.find_instance_center(heat.clone(), thr, k)
+    assert torch.equal(got, want)
+
+
+def test_peak_extract_and_smoothing_vs_torch_on_cuda(cl4):
+    from oracle import torch_ref as tr
+    from cl4wsis_b200.wss.utils import peak_extract_device, smoothing
+    g = torch.Generator(device="cpu").manual_seed(99)
+    heat = torch.rand((2, 20, 128, 96), generator=g).cuda()
+    sm = smoothing(heat, 3)
+    torch.testing.assert_close(sm, tr.smoothing(heat, 3), rtol=2e-6, atol=1e-7)
+    s, y, x = peak_extract_device(sm, 15, 25)
+    ws, wy, wx = tr.peak_extract(sm, 15, 25)
+    assert torch.equal(s, ws)                      # scores exact; random floats: no ties, so indices too
+    assert torch.equal(y, wy) and torch.equal(x, wx)
+
+
+# --------------------------------------------------------------------------- same images, sharded two ways
+def test_sharding_reproduces_the_single_gpu_result(cl4):
+    """images are independent, so a batch split across ranks must give exactly what one GPU gives.
+    One GPU plays both ranks: images 0..7 as one batch of 8 vs two shards of 4 (bench.py seeds synthetic images by GLOBAL
+    image index); refined masks, ids and centre counts must be bit-identical and the checksums equal."""
+    import bench
+    cfg = dict(B=8, C=21, H=128, W=128, dil=[1, 2, 4, 8, 12, 24], T=10, Kc=5, nms=41, thr=0.3)
+    full = [t.cuda() for t in bench.synth_inputs(cfg, first_image=0, n_images=8)]
+    step8 = cl4.PseudoLabelStep(8, 21, 128, 128, num_iter=10, threshold=0.3, nms_kernel=41)
+    r8, i8, c8, _ = (t.clone() for t in step8.run(*full))
+    step4 = cl4.PseudoLabelStep(4, 21, 128, 128, num_iter=10, threshold=0.3, nms_kernel=41)
+    ck = 0.0
+    for rank in range(2):
+        shard = [t.cuda() for t in bench.synth_inputs(cfg, first_image=4 * rank, n_images=4)]
+        for a, b in zip(shard, full):
+            assert torch.equal(a, b[4 * rank:4 * rank + 4])
+        r4, i4, c4, _ = step4.run(*shard)
+        assert torch.equal(r4, r8[4 * rank:4 * rank + 4])
+        assert torch.equal(i4, i8[4 * rank:4 * rank + 4])
+        assert torch.equal(c4, c8[4 * rank:4 * rank + 4])
+        ck += float(i4.double().sum())
+    assert ck == float(i8.double().sum())

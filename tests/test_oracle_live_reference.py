@@ -103,3 +103,33 @@ def test_phase1_pieces_random_shapes(ref):
         for amb, top, bkg, low in [(True, 0.6, 0.7, 0.2), (False, 0.6, 0.6, 0.2), (True, 0.9, 0.1, 0.0), (True, 0.3, 0.3, 0.9)]:
             want = pseudo_gtmask(torch.from_numpy(gated.copy()), ambiguous=amb, cutoff_top=top, cutoff_bkg=bkg, cutoff_low=low).numpy()
             assert np.array_equal(p1.pseudo_gtmask(gated, amb, top, bkg, low), want), (B, C, amb, top, bkg, low)
+
+
+def test_torch_ref_matches_live_reference(ref):
+    """oracle/torch_ref.py (the stock-PyTorch restatement that travels to the GPU box as second oracle and second
+    baseline) against the reference's own modules on CPU tensors: PAMR bit-exact (same ATen ops in the same order),
+    centre lists, instance ids, peaks and smoothing exact."""
+    import torch
+    from oracle import torch_ref as tr
+    wm, wu, mu, mg = ref
+    rng = np.random.default_rng(23)
+    for (B, C, H, W, dil, T) in [(2, 3, 40, 56, [1, 2, 4, 8, 12, 24], 10), (1, 5, 33, 47, [1, 2, 4, 8, 12], 3), (1, 2, 24, 24, [1, 3], 1)]:
+        x = torch.from_numpy(mg.natural_image(rng, B, H, W))
+        m = torch.from_numpy(mg.soft_mask(rng, B, C, H // 2, W // 2))   # exercises the align_corners resize too
+        with torch.no_grad():
+            want = wm.PAMR(T, dil)(x, m)
+        assert torch.equal(tr.pamr(x, m, T, dil), want)
+    for (H, W, n, thr, k) in [(64, 80, 9, 0.3, 41), (40, 40, 20, 0.1, 3), (33, 65, 4, 0.5, 7)]:
+        heat, _ = mg.gaussian_heat(rng, H, W, n)
+        heat = np.round(heat * 64) / 64
+        want = mu.find_instance_center(torch.from_numpy(heat[None, None].copy()), thr, k, None)
+        got = tr.find_instance_center(torch.from_numpy(heat[None, None].copy()), thr, k)
+        assert torch.equal(got, want)
+        off = torch.from_numpy((rng.standard_normal((1, 2, H, W)) * 20).astype(np.float32))
+        if want.shape[0]:
+            assert torch.equal(tr.group_pixels(want, off), mu.group_pixels(want, off))
+    heat = torch.from_numpy(rng.random((2, 3, 48, 40)).astype(np.float32))
+    ws, wy, wx = wu.peak_extract(heat, 5, 10)
+    gs, gy, gx = tr.peak_extract(heat, 5, 10)
+    assert np.array_equal(gs.numpy(), ws) and np.array_equal(gy.numpy(), wy) and np.array_equal(gx.numpy(), wx)
+    assert torch.equal(tr.smoothing(heat, 3), wu.smoothing(heat, 3))
