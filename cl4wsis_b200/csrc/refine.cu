@@ -385,8 +385,9 @@ __global__ void ref_merge_clusters_kernel(const float* __restrict__ center, RefD
 }
 
 // ---- 4. grouping: nearest centre of the pixel's contour, group_pixels arithmetic (:523-540)
+// empty_id: the id of every pixel of a contour without any centre -- 0 (`ignore`: zeros_like(fg)) or 1 (fg.long()), :597-600
 __global__ void ref_group_kernel(const float* __restrict__ offsets, RefDims d, const int* __restrict__ comp_all,
-                                 RefComp* __restrict__ comps, unsigned char* __restrict__ ids) {
+                                 RefComp* __restrict__ comps, unsigned char* __restrict__ ids, int empty_id) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (i >= d.HW) return;
@@ -413,6 +414,9 @@ __global__ void ref_group_kernel(const float* __restrict__ offsets, RefDims d, c
             }
             id = (unsigned char)(best_k + 1);
             atomicMax(&c.n_ins, best_k + 1);  // n_ins = ins_seg.max()  (:332)
+        } else if (empty_id) {
+            id = (unsigned char)empty_id;
+            if (c.n_ins < empty_id) atomicMax(&c.n_ins, empty_id);
         }
     }
     ids[o + i] = id;
@@ -665,6 +669,348 @@ __global__ void pl_write_kernel(RefDims d, const int* __restrict__ comp_all, con
     out_offset[(size_t)b * 2 * d.HW + d.HW + i] = ox;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// get_ins_map (dataset/utils.py:795-902, Trainer.validate -> train.py:622) for one image on the device.
+//
+// The reference: softmax, flip test-time augmentation, label cleaning, argmax on the device; then per class one cv2 call
+// on the host, and per contour get_instance_segmentation plus several .item() reads per instance.  Here: one pass over
+// the pixels (im_prepare_kernel), the contour / NMS / clustering / grouping kernels of refine_label_generation above with
+// min_area 50 and the validation thresholds, per-(contour, id) statistics, and ONE block that orders the contours as
+// the reference visits them (class ascending, then OpenCV's label order) and numbers the instances.  The host reads the
+// instance count once, then cl4_ins_masks writes the [n, H, W] boolean masks.
+constexpr int kImMaxInst = 4096;           // instances per image in the output table
+constexpr int kImMaxG = 2 * kRefListCap;   // centres of all contours together (NMS centres <= kRefListCap, + cluster centres, + one
+                                           // pseudo centre per contour that has none when ignore is off)
+
+// Unlike the training path (at most 64 centres per contour, then the per-contour fallback), validation runs with small NMS
+// kernels on noisy heat maps: a contour may hold hundreds of NMS centres of which only a few attract pixels.  So the
+// centres of a contour are a RANGE of one per-image array: nms_sorted[nbase[s] .. + n_nms[s]) in raster order, followed by the
+// contour's accepted cluster centres (RefComp::ctr, at most kRefMaxCtr); a centre's global index gbase[s] + k (k = id - 1)
+// addresses the per-instance statistics.
+struct ImScratch {
+    float *pmax, *center_avg, *ones;
+    int *cslot, *crank, *nms_sorted, *nbase, *gbase, *gcount, *gidx, *minx, *rank, *icnt;
+    double* ipsum;
+    unsigned long long* ikey;
+    size_t bytes;
+};
+
+static ImScratch im_layout(char* base, size_t off, int C, int H, int W) {
+    ImScratch r;
+    auto take = [&](size_t bytes) {
+        char* p = base ? base + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    const size_t n = (size_t)H * W;
+    r.pmax = reinterpret_cast<float*>(take(n * 4));
+    r.center_avg = reinterpret_cast<float*>(take(n * 4 * C));
+    r.ones = reinterpret_cast<float*>(take((size_t)C * 4));
+    r.cslot = reinterpret_cast<int*>(take((size_t)kRefListCap * 4));
+    r.crank = reinterpret_cast<int*>(take((size_t)kRefListCap * 4));
+    r.nms_sorted = reinterpret_cast<int*>(take((size_t)kRefListCap * 4));
+    r.nbase = reinterpret_cast<int*>(take((size_t)kRefMaxComp * 4));
+    r.gbase = reinterpret_cast<int*>(take((size_t)kRefMaxComp * 4));
+    r.gcount = reinterpret_cast<int*>(take((size_t)kRefMaxComp * 4));
+    r.gidx = reinterpret_cast<int*>(take(n * 4));
+    r.rank = reinterpret_cast<int*>(take((size_t)kImMaxG * 4));
+    // icnt, ipsum, ikey are contiguous (one memset); minx is filled with 0x7f bytes
+    r.icnt = reinterpret_cast<int*>(take((size_t)kImMaxG * 4));
+    r.ipsum = reinterpret_cast<double*>(take((size_t)kImMaxG * 8));
+    r.ikey = reinterpret_cast<unsigned long long*>(take((size_t)kImMaxG * 8));
+    r.minx = reinterpret_cast<int*>(take((size_t)kRefMaxComp * 4));
+    r.bytes = off;
+    return r;
+}
+
+// softmax over the C+1 channels of each test-time view (:818), average with the mirrored second view (:823-825), label
+// cleaning (:835), argmax (:837, first maximum); the offsets of view 0 are rescaled IN PLACE as the reference does (:831-832).
+__global__ void __launch_bounds__(256)
+im_prepare_kernel(const float* __restrict__ seg, const float* __restrict__ center, float* offset0,
+                  const float* __restrict__ cls_label, int flip, float scale_y, float scale_x, RefDims d,
+                  long long* __restrict__ seg_map, float* __restrict__ pmax, float* __restrict__ center_avg,
+                  float* __restrict__ ones) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d.C) ones[i] = 1.f;
+    if (i >= d.HW) return;
+    const int y = i / d.W, x = i - y * d.W;
+    const int im = y * d.W + (d.W - 1 - x);  // the same pixel in the mirrored view
+    const float* s0 = seg + i;
+    const float* s1 = seg + (size_t)(d.C + 1) * d.HW + im;
+    float mx0 = s0[0], mx1 = flip ? s1[0] : 0.f;
+    for (int k = 1; k <= d.C; ++k) {
+        mx0 = fmaxf(mx0, s0[(size_t)k * d.HW]);
+        if (flip) mx1 = fmaxf(mx1, s1[(size_t)k * d.HW]);
+    }
+    float z0 = 0.f, z1 = 0.f;
+    for (int k = 0; k <= d.C; ++k) {
+        z0 += expf(s0[(size_t)k * d.HW] - mx0);
+        if (flip) z1 += expf(s1[(size_t)k * d.HW] - mx1);
+    }
+    float best = 0.f;
+    int arg = 0;
+    for (int k = 0; k <= d.C; ++k) {
+        float p = expf(s0[(size_t)k * d.HW] - mx0) / z0;
+        if (flip) p = (p + expf(s1[(size_t)k * d.HW] - mx1) / z1) / 2.f;
+        if (cls_label && k >= 1) p *= cls_label[k - 1];
+        if (k == 0 || p > best || (p != p && best == best)) {  // torch.argmax: first maximum, NaN counts as the largest
+            best = p;
+            arg = k;
+        }
+    }
+    seg_map[i] = arg;
+    pmax[i] = best;  // = seg_prob[cls + 1] at every pixel of a contour of class cls
+    if (flip) {
+        for (int c = 0; c < d.C; ++c)
+            center_avg[(size_t)c * d.HW + i] = (center[(size_t)c * d.HW + i] + center[(size_t)(d.C + c) * d.HW + im]) / 2.f;
+    }
+    offset0[i] = offset0[i] * scale_y;
+    offset0[d.HW + i] = offset0[d.HW + i] * scale_x;
+}
+
+// NMS centres of the ordered per-image list: contour slot and rank inside the contour (raster order)
+__global__ void im_assign_kernel(RefDims d, const int* __restrict__ comp, const long long* __restrict__ list,
+                                 const int* __restrict__ count, RefComp* __restrict__ comps, int* __restrict__ cslot,
+                                 int* __restrict__ crank, int* __restrict__ status) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = count[0];
+    if (j == 0 && n > kRefListCap) atomicOr(status, kRefListOverflow);
+    if (j >= min(n, kRefListCap)) return;
+    const int p = (int)list[2 * j] * d.W + (int)list[2 * j + 1];
+    const int s = comp[p];
+    int rank = 0;
+    for (int i = 0; i < j; ++i) rank += (comp[(int)list[2 * i] * d.W + (int)list[2 * i + 1]] == s);
+    cslot[j] = s;
+    crank[j] = rank;
+    atomicAdd(&comps[s].n_nms, 1);
+}
+
+// one block: exclusive scan over the contour slots of `what` (0: n_nms -> nbase; 1: max(n_nms + n_cl, empty_id) -> gbase, gcount)
+__global__ void __launch_bounds__(kRefMaxComp)
+im_scan_kernel(const RefComp* __restrict__ comps, const int* __restrict__ ncomp, int what, int empty_id, int* __restrict__ base,
+               int* __restrict__ cnt_out, int* __restrict__ status) {
+    __shared__ int pre[kRefMaxComp];
+    const int t = threadIdx.x;
+    const int n = min(ncomp[0], kRefMaxComp);
+    int mine = 0;
+    if (t < n) mine = what == 0 ? comps[t].n_nms : max(comps[t].n_nms + comps[t].n_ctr, empty_id);
+    pre[t] = mine;
+    __syncthreads();
+    for (int off = 1; off < kRefMaxComp; off <<= 1) {
+        const int v = (t >= off) ? pre[t - off] : 0;
+        __syncthreads();
+        pre[t] += v;
+        __syncthreads();
+    }
+    base[t] = pre[t] - mine;
+    if (cnt_out) cnt_out[t] = mine;
+    if (t == kRefMaxComp - 1 && pre[t] > (what == 0 ? kRefListCap : kImMaxG)) atomicOr(status, kRefListOverflow);
+}
+
+__global__ void im_scatter_kernel(RefDims d, const long long* __restrict__ list, const int* __restrict__ count,
+                                  const int* __restrict__ cslot, const int* __restrict__ crank, const int* __restrict__ nbase,
+                                  int* __restrict__ nms_sorted) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= min(count[0], kRefListCap)) return;
+    nms_sorted[nbase[cslot[j]] + crank[j]] = (int)list[2 * j] * d.W + (int)list[2 * j + 1];
+}
+
+// merge of NMS and cluster centres, one thread per contour (dataset/utils.py:728-751 = modules/utils.py:569-592); the
+// accepted cluster centres go to RefComp::ctr[0 .. n_ctr)
+__global__ void im_merge_clusters_kernel(const float* __restrict__ center, RefDims d, const int* __restrict__ comp,
+                                         const int* __restrict__ area2, const unsigned long long* __restrict__ sx2,
+                                         const unsigned long long* __restrict__ sy2, const long long* __restrict__ cl_list,
+                                         const int* __restrict__ cl_count, float lo, float hi, const int* __restrict__ nms_sorted,
+                                         const int* __restrict__ nbase, RefComp* __restrict__ comps,
+                                         const int* __restrict__ ncomp, int* __restrict__ status) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= min(ncomp[0], kRefMaxComp)) return;
+    RefComp& c = comps[s];
+    const float* plane = center + (size_t)c.cls * d.HW;
+    const int n = c.n_nms;
+    const int* mine = nms_sorted + nbase[s];
+    int n_cl = 0;
+    auto consider = [&](int cy, int cx) {
+        const int q = cy * d.W + cx;
+        const float hc = (comp[q] == s) ? plane[q] : 0.f;  // contour-masked heat
+        if (!(hc > 0.05f)) return;
+        bool accept = (n == 0);
+        if (!accept) {
+            long long best = -1;
+            for (int j = 0; j < n; ++j) {
+                const long long dy = mine[j] / d.W - cy, dx = mine[j] % d.W - cx;
+                const long long d2 = dy * dy + dx * dx;
+                if (best < 0 || d2 < best) best = d2;
+            }
+            accept = best > 10000;
+        }
+        if (!accept) return;
+        if (n_cl < kRefMaxCtr) c.ctr[n_cl++] = q;
+        else atomicOr(status, kRefTooManyCentres);
+    };
+    const long long bg_area = (long long)d.HW - c.weak_cnt;  // OpenCV's label 0 (see ref_merge_clusters_kernel)
+    const float a0 = (float)bg_area;
+    if (lo < a0 && a0 < hi) {
+        const unsigned long long tot_x = (unsigned long long)d.H * ((unsigned long long)d.W * (d.W - 1) / 2);
+        const unsigned long long tot_y = (unsigned long long)d.W * ((unsigned long long)d.H * (d.H - 1) / 2);
+        consider((int)((double)(tot_y - c.weak_sy) / (double)bg_area), (int)((double)(tot_x - c.weak_sx) / (double)bg_area));
+    }
+    const int m = min(cl_count[0], kRefListCap);
+    if (s == 0 && cl_count[0] > kRefListCap) atomicOr(status, kRefListOverflow);
+    for (int i = 0; i < m; ++i) {
+        const int q = (int)cl_list[2 * i] * d.W + (int)cl_list[2 * i + 1];
+        if (comp[q] != s) continue;
+        const double a = (double)area2[q];
+        consider((int)((double)sy2[q] / a), (int)((double)sx2[q] / a));
+    }
+    c.n_ctr = n_cl;
+}
+
+// grouping (group_pixels arithmetic) over the contour's NMS centres, then its cluster centres; gidx = global centre index
+__global__ void im_group_kernel(const float* __restrict__ offsets, RefDims d, const int* __restrict__ comp,
+                                const RefComp* __restrict__ comps, const int* __restrict__ nms_sorted,
+                                const int* __restrict__ nbase, const int* __restrict__ gbase, int empty_id,
+                                int* __restrict__ gidx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.HW) return;
+    const int s = comp[i];
+    int g = -1;
+    if (s >= 0) {
+        const RefComp& c = comps[s];
+        const int n1 = c.n_nms, n = n1 + c.n_ctr;
+        if (n > 0) {
+            const int* mine = nms_sorted + nbase[s];
+            const int y = i / d.W, x = i - y * d.W;
+            const float ly = __fadd_rn((float)y, offsets[i]);
+            const float lx = __fadd_rn((float)x, offsets[d.HW + i]);
+            float best_d = 0.f;
+            int best_k = 0;
+            for (int k = 0; k < n; ++k) {
+                const int q = k < n1 ? mine[k] : c.ctr[k - n1];
+                const float dy = __fsub_rn((float)(q / d.W), ly), dx = __fsub_rn((float)(q % d.W), lx);
+                const float dd = __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+                if (k == 0 || dd < best_d) {
+                    best_d = dd;
+                    best_k = k;
+                }
+            }
+            g = gbase[s] + best_k;
+        } else if (empty_id) {
+            g = gbase[s];  // fg.long(): the whole contour is instance 1  (dataset/utils.py:756-759)
+        }
+    }
+    gidx[i] = g;
+}
+
+// per centre: pixel count, sum of the class probability, first arg-max of the contour's (marked) heat (:868-878)
+__global__ void im_stats_kernel(const float* __restrict__ center, const float* __restrict__ pmax, RefDims d,
+                                const int* __restrict__ comp, const int* __restrict__ gidx, const RefComp* __restrict__ comps,
+                                int* __restrict__ icnt, double* __restrict__ ipsum, unsigned long long* __restrict__ ikey,
+                                int* __restrict__ minx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.HW) return;
+    const int s = comp[i];
+    if (s < 0) return;
+    const RefComp& c = comps[s];
+    // OpenCV's label order (8-connectivity, 2 x 2 block scan): block row of the contour's first pixel, then the first block
+    // column of the contour inside that block row
+    if ((i / d.W) >> 1 == (c.root / d.W) >> 1) atomicMin(&minx[s], i % d.W);
+    const int o = gidx[i];
+    if (o < 0 || o >= kImMaxG) return;
+    float h = center[(size_t)c.cls * d.HW + i];
+    for (int j = 0; j < c.n_ctr; ++j)
+        if (c.ctr[j] == i) h = 1.f;  // accepted cluster centres read 1.0 (marked in place by the reference)
+    atomicAdd(&icnt[o], 1);
+    atomicAdd(&ipsum[o], (double)pmax[i]);
+    atomicMax(&ikey[o], ((unsigned long long)orderable(h) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i));
+}
+
+// One block: sort the contours by (class, OpenCV label order), number their non-empty instances in that order and emit the
+// table (label, score; :880-887).  rank[g] = index of centre g's instance in the output, -1 if it owns no pixel.
+__global__ void __launch_bounds__(kRefMaxComp)
+im_order_kernel(RefDims d, const RefComp* __restrict__ comps, const int* __restrict__ ncomp, const int* __restrict__ gbase,
+                const int* __restrict__ gcount, const int* __restrict__ icnt, const double* __restrict__ ipsum,
+                const unsigned long long* __restrict__ ikey, const int* __restrict__ minx, int* __restrict__ rank,
+                int* __restrict__ out_label, double* __restrict__ out_score, int* __restrict__ n_out, int* __restrict__ status) {
+    __shared__ unsigned long long key[kRefMaxComp];
+    __shared__ int pre[kRefMaxComp];
+    const int t = threadIdx.x;
+    const int n = min(ncomp[0], kRefMaxComp);
+    unsigned long long k = ~0ull;
+    if (t < n) {
+        const RefComp& c = comps[t];
+        k = ((unsigned long long)c.cls << 44) | ((unsigned long long)((c.root / d.W) >> 1) << 28) |
+            ((unsigned long long)(minx[t] >> 1) << 12) | (unsigned long long)t;
+    }
+    key[t] = k;
+    __syncthreads();
+    for (int size = 2; size <= kRefMaxComp; size <<= 1)  // bitonic sort, ascending
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const int j = t ^ stride;
+            if (j > t) {
+                const bool up = (t & size) == 0;
+                const unsigned long long a = key[t], b = key[j];
+                if ((a > b) == up) {
+                    key[t] = b;
+                    key[j] = a;
+                }
+            }
+            __syncthreads();
+        }
+    const int slot = (t < n) ? (int)(key[t] & 0xfffull) : -1;
+    int g0 = 0, g1 = 0, mine = 0;
+    if (slot >= 0) {
+        g0 = gbase[slot];
+        g1 = min(g0 + gcount[slot], kImMaxG);
+        for (int g = g0; g < g1; ++g) mine += icnt[g] > 0;  // `if mask.sum() > 0`  :866
+    }
+    pre[t] = mine;
+    __syncthreads();
+    for (int off = 1; off < kRefMaxComp; off <<= 1) {  // inclusive scan
+        const int v = (t >= off) ? pre[t - off] : 0;
+        __syncthreads();
+        pre[t] += v;
+        __syncthreads();
+    }
+    if (t == kRefMaxComp - 1) {
+        n_out[0] = pre[t];
+        if (pre[t] > kImMaxInst) atomicOr(status, kRefListOverflow);
+    }
+    if (slot < 0) return;
+    int idx = pre[t] - mine;
+    const int cls = comps[slot].cls;
+    for (int g = g0; g < g1; ++g) {
+        if (icnt[g] == 0) {
+            rank[g] = -1;
+            continue;
+        }
+        rank[g] = idx < kImMaxInst ? idx : -1;
+        if (idx < kImMaxInst) {
+            const double seg_score = (double)(float)(ipsum[g] / (double)icnt[g]);  // fp32 .mean().item()
+            double center_score = (double)unorderable((unsigned)(ikey[g] >> 32));
+            if (center_score >= 1.0) center_score = seg_score;  // clustered centre: conf = seg_score  (:882-883)
+            out_label[idx] = cls;
+            out_score[idx] = center_score * seg_score;
+        }
+        ++idx;
+    }
+}
+
+__global__ void im_pixel_map_kernel(RefDims d, const int* __restrict__ gidx, const int* __restrict__ rank,
+                                    int* __restrict__ inst_map) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.HW) return;
+    const int g = gidx[i];
+    inst_map[i] = (g >= 0 && g < kImMaxG) ? rank[g] : -1;
+}
+
+__global__ void im_masks_kernel(const int* __restrict__ inst_map, int n, int HW, unsigned char* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HW) return;
+    const int k = inst_map[i];
+    for (int j = blockIdx.y; j < n; j += gridDim.y) out[(size_t)j * HW + i] = (unsigned char)(j == k);
+}
+
 }  // namespace cl4
 
 extern "C" int cl4_pseudo_labels(const long long* seg_gt, const float* cls_label, const float* peak_conf,
@@ -781,7 +1127,7 @@ extern "C" int cl4_refine_labels(const float* seg_logits, const float* center, c
         center, d, sc.comp, sc.area, sc.sx, sc.sy, sc.list_cl, sc.cnt_cl, use_clusters, lo, hi, top_k, sc.comps, sc.ncomp,
         sc.status);
     // grouping, instance statistics, outputs
-    ref_group_kernel<<<lin, 256, 0, s>>>(offsets, d, sc.comp, sc.comps, sc.ids);
+    ref_group_kernel<<<lin, 256, 0, s>>>(offsets, d, sc.comp, sc.comps, sc.ids, 0);
     ref_inst_stats_kernel<<<lin, 256, 0, s>>>(seg_logits, center, label, d, sc.comp, sc.ids, max_inst, sc.comps);
     ref_finalize_kernel<<<dim3(ceil_div(kRefMaxComp * kRefMaxInst, 256), B), 256, 0, s>>>(d, refine_thresh, max_inst,
                                                                                           sc.comps, sc.ncomp);
@@ -789,4 +1135,82 @@ extern "C" int cl4_refine_labels(const float* seg_logits, const float* center, c
     ref_splat_kernel<<<dim3(kRefMaxComp, B), 256, 0, s>>>(d, gauss, sigma, max_inst, sc.comps, sc.ncomp, out_center);
     REF_CUDA(cudaMemcpyAsync(status_out, sc.status, 4, cudaMemcpyDeviceToDevice, s), "copy");
     return check_launch("refine");
+}
+
+extern "C" int cl4_ins_map_max_instances(void) { return cl4::kImMaxInst; }
+
+extern "C" size_t cl4_ins_map_scratch_bytes(int C, int H, int W) {
+    if (C <= 0 || H <= 0 || W <= 0) return 0;
+    const size_t base = cl4::ref_layout(nullptr, 1, H, W).bytes;
+    return cl4::im_layout(nullptr, base, C, H, W).bytes;
+}
+
+extern "C" int cl4_ins_map(const float* seg_logits, const float* center, float* offset0, const float* cls_label, int flip,
+                           float scale_y, float scale_x, float val_thresh, int val_kernel, float beta, int ignore, int min_area,
+                           long long* seg_map_out, int* inst_map_out, int* label_out, double* score_out, int* n_out,
+                           int* status_out, int C, int H, int W, void* scratch, size_t scratch_bytes, cl4_stream_t stream) {
+    using namespace cl4;
+    CL4_REQUIRE(C >= 1 && C < (1 << 19) && H > 0 && W > 0 && (long long)H * W < (1ll << 30) && H < 65536 && W < 65536, CL4_EINVAL,
+                "ins_map: bad shape");
+    CL4_REQUIRE(val_kernel > 0 && (val_kernel & 1), CL4_EINVAL, "ins_map: nms kernel must be odd and positive");
+    CL4_REQUIRE(val_thresh >= 0.f, CL4_EUNSUPPORTED, "ins_map: negative threshold");
+    CL4_REQUIRE(seg_logits && center && offset0 && seg_map_out && inst_map_out && label_out && score_out && n_out && status_out,
+                CL4_EINVAL, "ins_map: null pointer");
+    CL4_REQUIRE(scratch && scratch_bytes >= cl4_ins_map_scratch_bytes(C, H, W), CL4_ESCRATCH, "ins_map: scratch too small");
+    RefDims d{1, C, H, W, H * W};
+    RefScratch sc = ref_layout(reinterpret_cast<char*>(scratch), 1, H, W);
+    ImScratch im = im_layout(reinterpret_cast<char*>(scratch), sc.bytes, C, H, W);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int wpr = ceil_div(W, 32);
+    dim3 lin(ceil_div(d.HW, 256), 1), blk(32, 8), grd(ceil_div(W, 32), ceil_div(H, 8), 1), wgrid(ceil_div(wpr, 8), H, 1);
+
+    im_prepare_kernel<<<ceil_div(max(d.HW, C), 256), 256, 0, s>>>(seg_logits, center, offset0, cls_label, flip ? 1 : 0, scale_y,
+                                                                 scale_x, d, seg_map_out, im.pmax, im.center_avg, im.ones);
+    const float* heat = flip ? im.center_avg : center;
+    int rc = run_contours(seg_map_out, im.ones, d, min_area, sc, s);  // every class present in seg_map (:838)
+    if (rc != CL4_OK) return rc;
+    ref_nms_kernel<<<wgrid, 256, 0, s>>>(heat, d, sc.comp, sc.comps, val_thresh, (val_kernel - 1) / 2, wpr, sc.words);
+    rc = check_launch("ins_map nms");
+    if (rc != CL4_OK) return rc;
+    rc = launch_center_compact(sc.words, 1, H, wpr, sc.list_nms, sc.cnt_nms, kRefListCap, sc.row_off, s);
+    if (rc != CL4_OK) return rc;
+    const int lblk = ceil_div(kRefListCap, 256);
+    im_assign_kernel<<<lblk, 256, 0, s>>>(d, sc.comp, sc.list_nms, sc.cnt_nms, sc.comps, im.cslot, im.crank, sc.status);
+    im_scan_kernel<<<1, kRefMaxComp, 0, s>>>(sc.comps, sc.ncomp, 0, 0, im.nbase, nullptr, sc.status);
+    im_scatter_kernel<<<lblk, 256, 0, s>>>(d, sc.list_nms, sc.cnt_nms, im.cslot, im.crank, im.nbase, im.nms_sorted);
+    if (beta > 0.f) {  // centre clustering (cluster_peaks, dataset/utils.py:767-793)
+        const float lo = 21.f - beta, hi = 21.f + beta;
+        REF_CUDA(cudaMemsetAsync(sc.area, 0, (char*)sc.root - (char*)sc.area, s), "memset");
+        ref_weak_init_kernel<<<lin, 256, 0, s>>>(offset0, d, sc.comp, 2.5f, sc.root);
+        ref_weak_merge4_kernel<<<grd, blk, 0, s>>>(d, sc.comp, sc.root);
+        ref_weak_stats_kernel<<<grd, blk, 0, s>>>(d, sc.comp, sc.root, sc.area, sc.sx, sc.sy, sc.comps);
+        ref_weak_select_kernel<<<wgrid, 256, 0, s>>>(d, sc.root, sc.area, lo, hi, wpr, sc.words);
+        rc = check_launch("ins_map clusters");
+        if (rc != CL4_OK) return rc;
+        rc = launch_center_compact(sc.words, 1, H, wpr, sc.list_cl, sc.cnt_cl, kRefListCap, sc.row_off, s);
+        if (rc != CL4_OK) return rc;
+        im_merge_clusters_kernel<<<ceil_div(kRefMaxComp, 128), 128, 0, s>>>(heat, d, sc.comp, sc.area, sc.sx, sc.sy, sc.list_cl,
+                                                                            sc.cnt_cl, lo, hi, im.nms_sorted, im.nbase, sc.comps,
+                                                                            sc.ncomp, sc.status);
+    }
+    const int empty_id = ignore ? 0 : 1;
+    im_scan_kernel<<<1, kRefMaxComp, 0, s>>>(sc.comps, sc.ncomp, 1, empty_id, im.gbase, im.gcount, sc.status);
+    im_group_kernel<<<lin.x, 256, 0, s>>>(offset0, d, sc.comp, sc.comps, im.nms_sorted, im.nbase, im.gbase, empty_id, im.gidx);
+    REF_CUDA(cudaMemsetAsync(im.icnt, 0, (char*)im.minx - (char*)im.icnt, s), "memset");
+    REF_CUDA(cudaMemsetAsync(im.minx, 0x7f, (size_t)kRefMaxComp * 4, s), "memset");
+    im_stats_kernel<<<lin.x, 256, 0, s>>>(heat, im.pmax, d, sc.comp, im.gidx, sc.comps, im.icnt, im.ipsum, im.ikey, im.minx);
+    im_order_kernel<<<1, kRefMaxComp, 0, s>>>(d, sc.comps, sc.ncomp, im.gbase, im.gcount, im.icnt, im.ipsum, im.ikey, im.minx,
+                                              im.rank, label_out, score_out, n_out, sc.status);
+    im_pixel_map_kernel<<<lin.x, 256, 0, s>>>(d, im.gidx, im.rank, inst_map_out);
+    REF_CUDA(cudaMemcpyAsync(status_out, sc.status, 4, cudaMemcpyDeviceToDevice, s), "copy");
+    return check_launch("ins_map");
+}
+
+extern "C" int cl4_ins_masks(const int* inst_map, int n, int H, int W, unsigned char* masks_out, cl4_stream_t stream) {
+    using namespace cl4;
+    CL4_REQUIRE(n >= 0 && H > 0 && W > 0, CL4_EINVAL, "ins_masks: bad shape");
+    if (n == 0) return CL4_OK;
+    CL4_REQUIRE(inst_map && masks_out, CL4_EINVAL, "ins_masks: null pointer");
+    im_masks_kernel<<<dim3(ceil_div(H * W, 256), min(n, 64)), 256, 0, (cudaStream_t)stream>>>(inst_map, n, H * W, masks_out);
+    return check_launch("ins_masks");
 }

@@ -12,6 +12,7 @@ import io
 import numpy as np
 import torch
 
+from .. import _lib
 from ..modules import utils as _mu
 from ..modules.utils import group_pixels  # noqa: F401  (identical in both reference files)
 
@@ -36,7 +37,8 @@ def _opencv_label_order(comp, info, n):
     """Order of the contour slots of ONE class as cv2.connectedComponentsWithStats(connectivity=8)
     numbers them: OpenCV's 8-connectivity labelling scans 2x2 blocks in raster order, so labels follow
     (block row of the contour's first pixel, first block column of the contour inside that block row)
-    — pinned against cv2 in tests/test_abi_and_host.py."""
+    — pinned against cv2 in tests/test_abi_and_host.py.  (Host-side statement of the rule that
+    ``cl4_ins_map`` applies on the device; kept for that test.)"""
     H, W = comp.shape
     keys = []
     for s in n:
@@ -48,72 +50,62 @@ def _opencv_label_order(comp, info, n):
 
 
 def get_ins_map(out, cls_label, target_size, device, args):
-    """post-processing (output -> instance map) — dataset/utils.py:795-902.
+    """post-processing (output -> instance map) — dataset/utils.py:795-902, on the device.
 
     out: dict with 'seg' [B,C+1,H,W] logits, 'center' [B,C,H,W], 'offset' [B,2,H,W] (B = 2 with
     ``args.val_flip``); returns (seg_map [H,W] int64 ndarray, pred_label [n], pred_mask [n,H,W] bool,
-    pred_score [n]).  Like the reference it rescales ``out['offset'][0]`` IN PLACE (:826-828).
-    Contours come from the GPU (``cl4_contours8``) in OpenCV's label order, so the instance lists
-    are ordered as the reference's.  (The reference's empty-result branch uses ``np.bool``, which
-    newer numpy removed; ``np.bool_`` is used here.)
+    pred_score [n] float64), instances ordered as the reference's loops produce them.  Like the reference
+    it rescales ``out['offset'][0]`` IN PLACE (:831-832).  One ``cl4_ins_map`` call does the softmax, the
+    flip averaging, the label cleaning, the argmax, the contours of every class, per-contour centre NMS,
+    clustering, grouping and the per-instance scores; the host reads the instance count once and a second
+    launch writes the boolean masks.  (The reference's empty-result branch uses ``np.bool``, which newer
+    numpy removed; ``np.bool_`` is used here.)
+
+    Capacity (a clear error instead of a silently different answer): 1024 contours of >= 50 px, 4096 NMS
+    centres / cluster blobs / instances per image, 64 accepted cluster centres per contour; the number of NMS
+    centres inside one contour is not limited.
     """
-    pred_label, pred_mask, pred_score = [], [], []
-
-    seg_prob = torch.softmax(out['seg'].detach(), 1)
-    center_map = out['center'].detach()
-    offset_map = out['offset'][0].detach()
-
-    if args.val_flip:
-        seg_prob = (seg_prob[0] + seg_prob[1].flip(-1)) / 2.
-        center_map = (center_map[0] + center_map[1].flip(-1)) / 2.
-    else:
-        seg_prob = seg_prob[0]
-        center_map = center_map[0]
-
-    out_size = seg_prob.shape[1:]
-    offset_map[0, :, :] = offset_map[0, :, :] * (target_size[0] / out_size[0])
-    offset_map[1, :, :] = offset_map[1, :, :] * (target_size[1] / out_size[1])
-
+    lib = _lib.load()
+    seg, ctr, off = out['seg'].detach(), out['center'].detach(), out['offset']
+    for name, t in (("out['seg']", seg), ("out['center']", ctr), ("out['offset']", off)):
+        _lib.require_cuda(t, name)
+        if t.dtype != torch.float32:
+            raise TypeError(f"get_ins_map: {name} must be float32")
+    flip = bool(args.val_flip)
+    if seg.shape[0] < (2 if flip else 1):
+        raise IndexError("get_ins_map: val_flip needs the mirrored view as out[...][1]")
+    seg, ctr = seg.contiguous(), ctr.contiguous()
+    off0 = off.detach()[0]
+    if not off0.is_contiguous():
+        raise ValueError("get_ins_map: out['offset'][0] must be contiguous (it is rescaled in place)")
+    C, (H, W) = ctr.shape[1], seg.shape[-2:]
+    dev = seg.device
+    lab = None
     if args.val_clean:
-        seg_prob[1:, :, :] *= cls_label[0, :, None, None].to(device)
-
-    seg_map = torch.argmax(seg_prob, 0)
-    C = center_map.shape[0]
-
-    # 8-connected contours of every class present, on the device (the reference: one cv2 call per class)
-    comp, info, ncomp = _mu.contours8(seg_map[None], torch.ones((1, C), device=seg_map.device), min_area=MINIMUM_MASK_SIZE)
-    n = int(ncomp[0])
-    comp_h, info_h = comp[0].cpu().numpy(), info[0, :n].cpu().numpy()
-    center_map = center_map.float()
-    offset_f = offset_map.float()
-
-    for cls in sorted(set(int(c) for c in info_h[:, 1])):  # torch.unique(seg_map) - 1, ascending
-        slots = [s for s in range(n) if int(info_h[s, 1]) == cls]
-        for s in _opencv_label_order(comp_h, info_h, slots):
-            contour_mask = comp[0] == s
-            center_map_cls_roi = center_map[cls] * contour_mask
-            ins_map = get_instance_segmentation(contour_mask[None, ...], center_map_cls_roi[None, None, ...],
-                                                offset_f[None, ...], threshold=args.val_thresh,
-                                                nms_kernel=args.val_kernel, beta=args.beta, ignore=args.val_ignore)
-            ins_map = ins_map.squeeze(0)
-            n_ins = int(ins_map.max())
-            for id in range(1, n_ins + 1):
-                mask = (ins_map == id)
-                if mask.sum() > 0:
-                    index = torch.where(mask)
-                    center_idx = center_map_cls_roi[index].argmax()
-                    seg_score = seg_prob[cls + 1][index].mean().item()
-                    cy, cx = index[0][center_idx], index[1][center_idx]
-                    center_score = center_map_cls_roi[cy, cx].item()
-                    if center_score >= 1:  # clustered centre: conf = seg_score
-                        center_score = seg_score
-                    pred_label.append(cls)
-                    pred_mask.append(mask.cpu().numpy())
-                    pred_score.append(center_score * seg_score)
-
-    if len(pred_label) == 0:
-        pred_label.append(0)
-        pred_mask.append(np.zeros(target_size, dtype=np.bool_))
-        pred_score.append(0)
-
-    return seg_map.cpu().numpy(), np.stack(pred_label, 0), np.stack(pred_mask, 0), np.stack(pred_score, 0)
+        lab = cls_label[0].detach().to(device=dev, dtype=torch.float32).contiguous()
+    cap = lib.cl4_ins_map_max_instances()
+    with torch.cuda.device(dev):
+        seg_map = torch.empty((H, W), dtype=torch.int64, device=dev)
+        inst_map = torch.empty((H, W), dtype=torch.int32, device=dev)
+        labels = torch.empty(cap, dtype=torch.int32, device=dev)
+        scores = torch.empty(cap, dtype=torch.float64, device=dev)
+        head = torch.zeros(2, dtype=torch.int32, device=dev)          # [n, status]
+        nbytes = lib.cl4_ins_map_scratch_bytes(C, H, W)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        st = _lib.stream_ptr(dev)
+        _lib.check(lib.cl4_ins_map(_lib.ptr(seg), _lib.ptr(ctr), _lib.ptr(off0), _lib.ptr(lab), int(flip),
+                                   float(target_size[0] / H), float(target_size[1] / W), float(args.val_thresh),
+                                   int(args.val_kernel), float(args.beta), 1 if args.val_ignore else 0, MINIMUM_MASK_SIZE,
+                                   _lib.ptr(seg_map), _lib.ptr(inst_map), _lib.ptr(labels), _lib.ptr(scores),
+                                   _lib.ptr(head), _lib.ptr(head[1:]), C, H, W, _lib.ptr(scratch), nbytes, st), "get_ins_map")
+        n, status = head.tolist()                                       # the one host synchronisation
+        if status:
+            raise NotImplementedError(f"get_ins_map: capacity exceeded (status {status}: 1 = more than 1024 contours, "
+                                      f"2 = more than 64 cluster centres in a contour, 4 = more than {cap} centres or instances)")
+        if n == 0:
+            return (seg_map.cpu().numpy(), np.stack([0], 0), np.stack([np.zeros(tuple(target_size), dtype=np.bool_)], 0),
+                    np.stack([0], 0))
+        masks = torch.empty((n, H, W), dtype=torch.uint8, device=dev)
+        _lib.check(lib.cl4_ins_masks(_lib.ptr(inst_map), n, H, W, _lib.ptr(masks), st), "get_ins_map masks")
+    return (seg_map.cpu().numpy(), labels[:n].cpu().numpy().astype(np.int64), masks.cpu().numpy().astype(np.bool_),
+            scores[:n].cpu().numpy())

@@ -205,6 +205,31 @@ int cl4_refine_labels(const float* seg_logits, const float* center, const float*
                       int H, int W, void* scratch, size_t scratch_bytes, cl4_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
+ * get_ins_map — dataset/utils.py:795-902, the validation post-processing (Trainer.validate,
+ * train.py:622), for one image with no host round trip per class / contour / instance.
+ *
+ * cl4_ins_map: seg_logits [Bf,C+1,H,W], center [Bf,C,H,W] with Bf = 2 when `flip` (args.val_flip: the
+ * second view is mirrored and averaged in, :823-825) else 1; offset0 [2,H,W] = out['offset'][0], rescaled
+ * IN PLACE by scale_y = target_h / H and scale_x = target_w / W as the reference does (:831-832);
+ * cls_label [C] or NULL (args.val_clean, :835).  val_thresh / val_kernel / beta / ignore =
+ * args.val_thresh / val_kernel / beta / val_ignore; min_area = MINIMUM_MASK_SIZE of dataset/utils.py:147 (50).
+ * Outputs (device): seg_map_out [H,W] int64 (the argmax, :837); inst_map_out [H,W] int32 = index of the
+ * pixel's instance in the output lists or -1; label_out / score_out [cl4_ins_map_max_instances()] =
+ * pred_label / pred_score in the reference's order (class ascending, contours in OpenCV's label order,
+ * instance id ascending, empty ids skipped); n_out [1]; status_out [1]: 0 = done, otherwise a capacity
+ * limit was hit (1: > 1024 contours of >= min_area pixels; 2: > 64 accepted CLUSTER centres in one contour;
+ * 4: > 4096 NMS centres / cluster components / instances in the image).  NMS centres per contour are not limited.
+ * cl4_ins_masks: inst_map -> pred_mask [n,H,W] bytes (0/1).
+ * ------------------------------------------------------------------------- */
+int cl4_ins_map_max_instances(void);
+size_t cl4_ins_map_scratch_bytes(int C, int H, int W);
+int cl4_ins_map(const float* seg_logits, const float* center, float* offset0, const float* cls_label, int flip,
+                float scale_y, float scale_x, float val_thresh, int val_kernel, float beta, int ignore, int min_area,
+                long long* seg_map_out, int* inst_map_out, int* label_out, double* score_out, int* n_out,
+                int* status_out, int C, int H, int W, void* scratch, size_t scratch_bytes, cl4_stream_t stream);
+int cl4_ins_masks(const int* inst_map, int n, int H, int W, unsigned char* masks_out, cl4_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
  * Producers and consumers of PAMR inside the phase-1 step (train.py:372-385), SURVEY 8f rank 2.
  *
  * cl4_denorm: utils/utils.py:26-41 -- out = x * std[k] + mean[k] per RGB channel (two roundings, as

@@ -588,7 +588,7 @@ class _VArgs:
     pass
 
 
-@pytest.mark.parametrize("ci", [0, 1, 2])
+@pytest.mark.parametrize("ci", [0, 1, 2, 3, 4])
 def test_get_ins_map_golden(cl4, golden_more, ci):
     """dataset/utils.py:795-902 (Trainer.validate, train.py:622) against reference outputs: same
     instances in the same order, masks and labels bit-exact, scores to fp32 rounding."""
@@ -608,6 +608,59 @@ def test_get_ins_map_golden(cl4, golden_more, ci):
     assert pm.shape == shape and pm.dtype == np.bool_ and np.array_equal(pm, want_mask)
     np.testing.assert_allclose(ps, g[k + "pred_score"], rtol=2e-6, atol=0)
     assert np.array_equal(out["offset"].cpu().numpy(), g[k + "offset_after"])  # rescaled in place, as the reference
+
+
+@pytest.mark.parametrize("H,W,n_inst,flip,clean,ignore,kern,thr,beta,noise", [
+    (512, 512, 24, False, False, False, 41, 0.1, 3.0, 0.02),
+    (512, 512, 30, True, True, True, 41, 0.1, 3.0, 0.02),
+    (320, 480, 16, False, True, False, 7, 0.2, 5.0, 0.3),     # many centres per contour
+    (200, 333, 12, True, False, False, 41, 0.1, 5.0, 0.09),   # clustered centres, odd width
+])
+def test_get_ins_map_random_vs_oracle(cl4, oracle, H, W, n_inst, flip, clean, ignore, kern, thr, beta, noise):
+    """dataset/utils.py:795-902 at validation size against oracle/labelgen.get_ins_map (numpy + OpenCV, pinned to the
+    reference on the insmap fixtures): seg map, instance order, labels and masks bit-exact, scores to fp32 rounding."""
+    from cl4wsis_b200.dataset.utils import get_ins_map
+    rng = np.random.default_rng(H * 7 + n_inst)
+    C = 20
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    nb = 2 if flip else 1
+    segs, heats, offs = [], [], []
+    inst = [(int(rng.integers(0, C)), int(rng.integers(10, H - 10)), int(rng.integers(10, W - 10)),
+             int(rng.integers(4, H // 6)), int(rng.integers(4, W // 6))) for _ in range(n_inst)]
+    for v in range(nb):
+        gt = np.zeros((H, W), np.int64)
+        heat = (noise * rng.random((C, H, W))).astype(np.float32)
+        off = (0.3 * rng.standard_normal((2, H, W))).astype(np.float32) + 40.0
+        for i, (cls, cy, cx, ry, rx) in enumerate(inst):
+            m = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0
+            gt[m] = cls + 1
+            if i % 5 != 4:  # every fifth instance has no peak
+                heat[cls] = np.maximum(heat[cls], rng.uniform(0.5, 0.95) * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / 72.0).astype(np.float32))
+            off[0][m] = (cy - yy)[m] + 0.3 * rng.standard_normal(int(m.sum())).astype(np.float32)
+            off[1][m] = (cx - xx)[m] + 0.3 * rng.standard_normal(int(m.sum())).astype(np.float32)
+        seg = rng.standard_normal((C + 1, H, W)).astype(np.float32)
+        for c in range(C + 1):
+            seg[c][gt == c] += 3.0
+        if v == 1:  # the second view is the mirrored image
+            seg, heat, off = seg[..., ::-1].copy(), heat[..., ::-1].copy(), off[..., ::-1].copy()
+        segs.append(seg); heats.append(heat); offs.append(off)
+    o = {"seg": np.stack(segs), "center": np.stack(heats), "offset": np.stack(offs)}
+    cls_label = np.zeros((1, C), np.float32)
+    for it in inst[:-2]:
+        cls_label[0, it[0]] = 1
+    tgt = (H * 2, W + 17)
+    a = _VArgs()
+    a.val_thresh, a.val_kernel, a.beta, a.val_ignore, a.val_flip, a.val_clean = thr, kern, beta, ignore, flip, clean
+    w_seg, w_lab, w_mask, w_score, w_off = oracle.labelgen.get_ins_map(o["seg"], o["center"], o["offset"], cls_label, tgt, thr,
+                                                                        kern, beta, ignore, flip, clean)
+    out = {n: cuda(v) for n, v in o.items()}
+    seg_map, pl, pm, ps = get_ins_map(out, cuda(cls_label), tgt, torch.device("cuda"), a)
+    assert np.array_equal(seg_map, w_seg)
+    assert np.array_equal(pl, w_lab), (pl.tolist(), w_lab.tolist())
+    assert pm.dtype == np.bool_ and pm.shape == w_mask.shape and np.array_equal(pm, w_mask)
+    np.testing.assert_allclose(ps, w_score, rtol=2e-6, atol=0)
+    assert len(pl) > n_inst // 3
+    assert np.array_equal(out["offset"][0].cpu().numpy(), w_off)
 
 
 # --------------------------------------------------------------------------- phase-1 producers / consumers of PAMR

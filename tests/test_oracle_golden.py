@@ -180,3 +180,22 @@ def test_phase1_oracle_matches_reference(golden_more, name):
     assert np.array_equal(p1.gate_labels(k("pamr"), k("l1h")), k("gated"))
     assert np.array_equal(p1.pseudo_gtmask(k("gated"), True, 0.6, 0.7, 0.2), k("pseudo"))
     assert np.array_equal(p1.pseudo_gtmask(k("soft"), False), k("pseudo_noamb"))
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2, 3, 4])
+def test_get_ins_map_oracle_golden(golden_more, oracle, ci):
+    """oracle/labelgen.get_ins_map against the reference's get_ins_map (dataset/utils.py:795-902): plain, flip TTA +
+    label cleaning + ignore, empty, clustered centres (score = seg_score^2), many centres per contour."""
+    g = golden_more("insmap")
+    k = f"insmap_{ci}__"
+    thr, kern, beta, ign, flip, clean = g[k + "args"].tolist()
+    seg_map, pl, pm, ps, off = oracle.labelgen.get_ins_map(g[k + "seg"], g[k + "center"], g[k + "offset"], g[k + "cls_label"],
+                                                           tuple(int(v) for v in g[k + "target"]), thr, int(kern), beta,
+                                                           bool(ign), bool(flip), bool(clean))
+    assert np.array_equal(seg_map, g[k + "seg_map"])
+    assert np.array_equal(pl, g[k + "pred_label"])
+    shape = tuple(g[k + "pred_mask_shape"])
+    want = np.unpackbits(g[k + "pred_mask"], axis=-1)[..., :shape[-1]].astype(bool)
+    assert pm.shape == shape and np.array_equal(pm, want)
+    np.testing.assert_allclose(ps, g[k + "pred_score"], rtol=2e-6, atol=0)
+    assert np.array_equal(off, g[k + "offset_after"][0])
