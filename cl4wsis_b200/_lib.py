@@ -13,7 +13,6 @@ LIB_PATH = os.environ.get("CL4_LIB") or os.path.join(_HERE, "libcl4wsis_b200.so"
 
 CL4_OK, CL4_EINVAL, CL4_EUNSUPPORTED, CL4_ECUDA, CL4_ESCRATCH = 0, -1, -2, -3, -4
 MAX_DILATIONS = 8
-MAX_TOPK = 256
 
 _vp = ctypes.c_void_p
 _int = ctypes.c_int
@@ -36,6 +35,8 @@ SIGNATURES = {
                                       _int, _int, _vp, _vp, _vp]),
     "cl4_peak_extract_scratch_bytes": (_sz, [_int] * 6),
     "cl4_peak_extract": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _int, _int, _int, _int, _int, _int, _vp]),
+    "cl4_cam_normalize": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _vp]),
+    "cl4_peak_extract_upsampled": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _sz, _int, _int, _int, _int, _int, _int, _vp]),
     "cl4_center_nms_scratch_bytes": (_sz, [_int] * 3),
     "cl4_center_nms": (_int, [_vp, _flt, _flt, _int, _int, _int, _int, _vp, _vp, _int, _vp, _sz, _vp]),
     "cl4_ccl4_scratch_bytes": (_sz, [_int, _int]),

@@ -23,12 +23,50 @@ __host__ inline size_t nms_smem_bytes(int r) {
     return sizeof(float) * (size_t)nms_pitch(r) * (size_t)(kTileH + 2 * r + kTileH);
 }
 
+// Where a tile's values come from.  PlaneSrc: a plane in memory.  UpsampleSrc: the plane
+// F.interpolate(small, (H, W), mode="bilinear", align_corners=False) (train.py:431) evaluated on the fly from the small map
+// (which stays in L1/L2), so the up-sampled heat map is never written or read: ATen's upsample_bilinear2d arithmetic,
+// source index max(scale * (dst + 0.5) - 0.5, 0) with scale = in / out, the four taps combined row-wise then column-wise.
+struct PlaneSrc {
+    const float* p;
+    int W;
+    __device__ __forceinline__ float at(int y, int x) const { return __ldg(p + (size_t)y * W + x); }
+};
+struct UpsampleSrc {
+    const float* p;
+    int h, w;
+    float sy, sx;
+    __device__ __forceinline__ float at(int y, int x) const {
+        const float fy = fmaxf(fmaf(sy, (float)y + 0.5f, -0.5f), 0.f), fx = fmaxf(fmaf(sx, (float)x + 0.5f, -0.5f), 0.f);
+        const int y1 = (int)fy, x1 = (int)fx;
+        const int yp = (y1 < h - 1) ? w : 0, xp = (x1 < w - 1) ? 1 : 0;
+        const float ly = fy - (float)y1, lx = fx - (float)x1, hy = 1.f - ly, hx = 1.f - lx;
+        const float* q = p + (size_t)y1 * w + x1;
+        return hy * (hx * __ldg(q) + lx * __ldg(q + xp)) + ly * (hx * __ldg(q + yp) + lx * __ldg(q + yp + xp));
+    }
+};
+struct PeakInput {  // h == 0: heat is [planes][H][W]; otherwise heat is [planes][h][w] and is up-sampled to H x W on the fly
+    const float* heat;
+    int H, W, h, w;
+    float sy, sx;
+};
+template <class Src>
+__device__ __forceinline__ Src make_src(const PeakInput& in, int plane_id);
+template <>
+__device__ __forceinline__ PlaneSrc make_src<PlaneSrc>(const PeakInput& in, int plane_id) {
+    return PlaneSrc{in.heat + (size_t)plane_id * in.H * in.W, in.W};
+}
+template <>
+__device__ __forceinline__ UpsampleSrc make_src<UpsampleSrc>(const PeakInput& in, int plane_id) {
+    return UpsampleSrc{in.heat + (size_t)plane_id * in.h * in.w, in.h, in.w, in.sy, in.sx};
+}
+
 // Stage the tile (optionally thresholded: v <= thr -> -1, F.threshold semantics) and
 // leave in s_col[ty][tx + r] ... the k x k window maximum for every tile pixel.
 // Returns through s_in / s_max: centre value at s_in[(ty+r)*pitch + tx+r],
 // pooled value at s_max[ty*pitch + tx].
-template <bool kThreshold>
-__device__ __forceinline__ void tile_maxpool(const float* __restrict__ plane, int H, int W, int y0, int x0, int r,
+template <bool kThreshold, class Src>
+__device__ __forceinline__ void tile_maxpool(const Src& src, int H, int W, int y0, int x0, int r,
                                              float thr, float* s_in, float* s_col) {
     const int pitch = nms_pitch(r);
     const int tw = kTileW + 2 * r, th = kTileH + 2 * r;
@@ -37,7 +75,7 @@ __device__ __forceinline__ void tile_maxpool(const float* __restrict__ plane, in
         const int y = y0 + ty - r, x = x0 + tx - r;
         float v = -INFINITY;
         if (y >= 0 && y < H && x >= 0 && x < W) {
-            v = __ldg(plane + (size_t)y * W + x);
+            v = src.at(y, x);
             if (kThreshold) v = (v <= thr) ? -1.f : v;
         }
         s_in[ty * pitch + tx] = v;
@@ -109,8 +147,8 @@ struct FastTile {
     static constexpr int kRun = 8;                            // rows per vertical task
 
     // s_key: staged keys, s_col: column-wise window maxima for all kCols columns
-    template <bool kThreshold>
-    __device__ static void stage_and_columns(const float* __restrict__ plane, int H, int W, int y0, int x0, float thr,
+    template <bool kThreshold, class Src>
+    __device__ static void stage_and_columns(const Src& src, int H, int W, int y0, int x0, float thr,
                                              int* s_key, int* s_col) {
         // a warp per staged row, lanes over its columns: coalesced loads, no integer division; all loads
         // of a warp are issued before the first one is consumed
@@ -121,11 +159,10 @@ struct FastTile {
         for (int q = 0; q < kRowsPerWarp; ++q) {
             const int y = y0 + warp_ + q * kWarpsPerBlock - R;
             const bool row_in = (warp_ + q * kWarpsPerBlock < kRows) && y >= 0 && y < H;
-            const float* prow = plane + (size_t)(row_in ? y : 0) * W;
 #pragma unroll
             for (int it = 0; it < kIts; ++it) {
                 const int x = x0 + it * 32 + lane_ - R;
-                v[q][it] = (row_in && it * 32 + lane_ < kCols && x >= 0 && x < W) ? __ldg(prow + x) : -INFINITY;
+                v[q][it] = (row_in && it * 32 + lane_ < kCols && x >= 0 && x < W) ? src.at(y, x) : -INFINITY;
             }
         }
 #pragma unroll
@@ -187,7 +224,7 @@ center_flags_fast_kernel(const float* __restrict__ heat, float thr, float min_va
     int* s_col = smem_i + T::kPitch * T::kRows;
     const int n = blockIdx.z;
     const int y0 = blockIdx.y * kTileH, x0 = blockIdx.x * kTileW;
-    T::template stage_and_columns<true>(heat + (size_t)n * H * W, H, W, y0, x0, thr, s_key, s_col);
+    T::template stage_and_columns<true>(PlaneSrc{heat + (size_t)n * H * W, W}, H, W, y0, x0, thr, s_key, s_col);
 
     // thread -> (row, 4-pixel group): lanes 0-15 one row, lanes 16-31 the next; two passes cover 32 rows
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -227,7 +264,7 @@ center_flags_kernel(const float* __restrict__ heat, float thr, float min_value, 
     const int n = blockIdx.z;
     const int y0 = blockIdx.y * kTileH, x0 = blockIdx.x * kTileW;
     const float* plane = heat + (size_t)n * H * W;
-    tile_maxpool<true>(plane, H, W, y0, x0, r, thr, s_in, s_col);
+    tile_maxpool<true>(PlaneSrc{plane, W}, H, W, y0, x0, r, thr, s_in, s_col);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // each warp owns rows warp, warp+8, ...; two 32-wide words per row
@@ -424,11 +461,13 @@ struct WarpTopK {
     }
 };
 
-// Pass 1: per tile, NMS then the tile's best K keys -> cand[plane][tile][K].
-template <int KPL>
+// Pass 1: per tile, NMS then the tile's best K keys -> cand[plane][tile][K].  `bound` (K > 256, selection in rounds of 256):
+// only keys below bound[plane], the last key of the previous round, take part.
+template <int KPL, class Src>
 __global__ void __launch_bounds__(kNmsThreads)
-peak_tile_kernel(const float* __restrict__ heat, int r, int H, int W, int K, int tiles_x, int tiles_per_plane,
+peak_tile_kernel(const PeakInput in, int r, int K, int tiles_x, int tiles_per_plane, const unsigned long long* __restrict__ bound,
                  unsigned long long* __restrict__ cand) {
+    const int H = in.H, W = in.W;
     extern __shared__ float smem[];
     const int pitch = nms_pitch(r);
     float* s_in = smem;
@@ -436,8 +475,8 @@ peak_tile_kernel(const float* __restrict__ heat, int r, int H, int W, int K, int
     const int plane_id = blockIdx.y;
     const int tile = blockIdx.x;
     const int y0 = (tile / tiles_x) * kTileH, x0 = (tile % tiles_x) * kTileW;
-    const float* plane = heat + (size_t)plane_id * H * W;
-    tile_maxpool<false>(plane, H, W, y0, x0, r, 0.f, s_in, s_col);
+    tile_maxpool<false>(make_src<Src>(in, plane_id), H, W, y0, x0, r, 0.f, s_in, s_col);
+    const unsigned long long below = bound ? bound[plane_id] : ~0ull;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpTopK<KPL> top;
@@ -454,6 +493,7 @@ peak_tile_kernel(const float* __restrict__ heat, int r, int H, int W, int K, int
                 const float m = row_window_max(s_col, pitch, ty, tx, r);
                 const float peak = __fmul_rn(v, (m == v) ? 1.f : 0.f);  // heat * keep (wss/utils.py:11-13)
                 key = make_key(peak, (uint32_t)(y * W + x));
+                if (key >= below) key = 0ull;
             }
             top.offer(key, lane);
         }
@@ -478,18 +518,18 @@ peak_tile_kernel(const float* __restrict__ heat, int r, int H, int W, int K, int
 }
 
 // Fast variant of pass 1 for compile-time radii (see FastTile).
-template <int KPL, int R>
+template <int KPL, int R, class Src>
 __global__ void __launch_bounds__(kNmsThreads)
-peak_tile_fast_kernel(const float* __restrict__ heat, int H, int W, int K, int tiles_x, int tiles_per_plane,
-                      unsigned long long* __restrict__ cand) {
+peak_tile_fast_kernel(const PeakInput in, int K, int tiles_x, int tiles_per_plane, unsigned long long* __restrict__ cand) {
     using T = FastTile<R>;
+    const int H = in.H, W = in.W;
     extern __shared__ __align__(16) int smem_i[];
     int* s_key = smem_i;
     int* s_col = smem_i + T::kPitch * T::kRows;
     const int plane_id = blockIdx.y;
     const int tile = blockIdx.x;
     const int y0 = (tile / tiles_x) * kTileH, x0 = (tile % tiles_x) * kTileW;
-    T::template stage_and_columns<false>(heat + (size_t)plane_id * H * W, H, W, y0, x0, 0.f, s_key, s_col);
+    T::template stage_and_columns<false>(make_src<Src>(in, plane_id), H, W, y0, x0, 0.f, s_key, s_col);
 
     // peak = heat * keep (wss/utils.py:11-13) is exactly 0 for almost every pixel (everything that is
     // not a local maximum), and all those zeros tie on the score: among them only the K lowest flat
@@ -588,7 +628,7 @@ peak_tile_fast_kernel(const float* __restrict__ heat, int H, int W, int K, int t
 template <int KPL>
 __global__ void __launch_bounds__(32)
 peak_merge_kernel(const unsigned long long* __restrict__ cand, int n_cand, int K, int W, float* __restrict__ scores,
-                  int* __restrict__ ys, int* __restrict__ xs) {
+                  int* __restrict__ ys, int* __restrict__ xs, int out_stride, int out_off, unsigned long long* __restrict__ bound) {
     const int plane_id = blockIdx.x;
     const int lane = threadIdx.x;
     const unsigned long long* src = cand + (size_t)plane_id * n_cand;
@@ -604,7 +644,8 @@ peak_merge_kernel(const unsigned long long* __restrict__ cand, int n_cand, int K
         if (gi < K) {
             const unsigned long long key = top.k[i];
             const uint32_t idx = key_index(key);
-            const size_t o = (size_t)plane_id * K + gi;
+            const size_t o = (size_t)plane_id * out_stride + out_off + gi;
+            if (bound && gi == K - 1) bound[plane_id] = key;  // the next round selects below this key
             scores[o] = key_score(key);
             ys[o] = (int)__fdiv_rn((float)idx, (float)W);  // (inds / W).int()  (wss/utils.py:18)
             xs[o] = (int)(idx % (uint32_t)W);              // inds % W          (wss/utils.py:19)
@@ -612,54 +653,80 @@ peak_merge_kernel(const unsigned long long* __restrict__ cand, int n_cand, int K
     }
 }
 
-template <int KPL, int R>
-static int launch_peak_tile_fast_R(const float* heat, unsigned long long* cand, int planes, int H, int W, int K,
-                                   int tiles_x, int tiles, cudaStream_t s) {
+template <int KPL, int R, class Src>
+static int launch_peak_tile_fast_R(const PeakInput& in, unsigned long long* cand, int planes, int K, int tiles_x, int tiles,
+                                   cudaStream_t s) {
     size_t smem = FastTile<R>::kSmem;
     const size_t need_keys = sizeof(unsigned long long) * kWarpsPerBlock * 32 * KPL;
     if (smem < need_keys) smem = need_keys;
-    cudaError_t e = cudaFuncSetAttribute(peak_tile_fast_kernel<KPL, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(peak_tile_fast_kernel<KPL, R, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         set_error("peak_extract: smem attribute: %s", cudaGetErrorString(e));
         return CL4_ECUDA;
     }
-    peak_tile_fast_kernel<KPL, R><<<dim3(tiles, planes), kNmsThreads, smem, s>>>(heat, H, W, K, tiles_x, tiles, cand);
+    peak_tile_fast_kernel<KPL, R, Src><<<dim3(tiles, planes), kNmsThreads, smem, s>>>(in, K, tiles_x, tiles, cand);
     return check_launch("peak_tile_fast");
 }
 // returns 1 when the radius has no fast specialisation
-template <int KPL>
-static int launch_peak_tile_fast(const float* heat, unsigned long long* cand, int planes, int H, int W, int r, int K,
-                                 int tiles_x, int tiles, cudaStream_t s) {
+template <int KPL, class Src>
+static int launch_peak_tile_fast(const PeakInput& in, unsigned long long* cand, int planes, int r, int K, int tiles_x, int tiles,
+                                 cudaStream_t s) {
     switch (r) {
-        case 1: return launch_peak_tile_fast_R<KPL, 1>(heat, cand, planes, H, W, K, tiles_x, tiles, s);
-        case 2: return launch_peak_tile_fast_R<KPL, 2>(heat, cand, planes, H, W, K, tiles_x, tiles, s);
-        case 7: return launch_peak_tile_fast_R<KPL, 7>(heat, cand, planes, H, W, K, tiles_x, tiles, s);
-        case 20: return launch_peak_tile_fast_R<KPL, 20>(heat, cand, planes, H, W, K, tiles_x, tiles, s);
+        case 1: return launch_peak_tile_fast_R<KPL, 1, Src>(in, cand, planes, K, tiles_x, tiles, s);
+        case 2: return launch_peak_tile_fast_R<KPL, 2, Src>(in, cand, planes, K, tiles_x, tiles, s);
+        case 7: return launch_peak_tile_fast_R<KPL, 7, Src>(in, cand, planes, K, tiles_x, tiles, s);
+        case 20: return launch_peak_tile_fast_R<KPL, 20, Src>(in, cand, planes, K, tiles_x, tiles, s);
     }
     return 1;
 }
 
-template <int KPL>
-static int launch_peak(const float* heat, float* scores, int* ys, int* xs, unsigned long long* cand, int B, int C,
-                       int H, int W, int r, int K, cudaStream_t s) {
-    const int tiles_x = ceil_div(W, kTileW), tiles_y = ceil_div(H, kTileH);
+constexpr int kPeakRound = 256;  // keys one selection round can hold (WarpTopK<8>)
+
+// K <= 256: one tile pass + one merge.  K > 256: rounds of 256 with the generic tile kernel; round j selects, among the keys
+// below the last key of round j-1 (keys are unique: they contain the pixel index), the next 256.
+template <int KPL, class Src>
+static int launch_peak(const PeakInput& in, float* scores, int* ys, int* xs, unsigned long long* cand, int planes, int r, int K,
+                       cudaStream_t s) {
+    const int tiles_x = ceil_div(in.W, kTileW), tiles_y = ceil_div(in.H, kTileH);
     const int tiles = tiles_x * tiles_y;
     size_t smem = nms_smem_bytes(r);
     const size_t need_keys = sizeof(unsigned long long) * kWarpsPerBlock * 32 * KPL;
     if (smem < need_keys) smem = need_keys;
-    cudaError_t e = cudaFuncSetAttribute(peak_tile_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(peak_tile_kernel<KPL, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         set_error("peak_extract: smem attribute: %s", cudaGetErrorString(e));
         return CL4_ECUDA;
     }
-    int rc = launch_peak_tile_fast<KPL>(heat, cand, B * C, H, W, r, K, tiles_x, tiles, s);
-    if (rc == 1) {  // no compile-time specialisation for this radius: generic kernel
-        peak_tile_kernel<KPL><<<dim3(tiles, B * C), kNmsThreads, smem, s>>>(heat, r, H, W, K, tiles_x, tiles, cand);
-        rc = check_launch("peak_tile");
+    if (K <= kPeakRound) {
+        int rc = launch_peak_tile_fast<KPL, Src>(in, cand, planes, r, K, tiles_x, tiles, s);
+        if (rc == 1) {  // no compile-time specialisation for this radius: generic kernel
+            peak_tile_kernel<KPL, Src><<<dim3(tiles, planes), kNmsThreads, smem, s>>>(in, r, K, tiles_x, tiles, nullptr, cand);
+            rc = check_launch("peak_tile");
+        }
+        if (rc != CL4_OK) return rc;
+        peak_merge_kernel<KPL><<<planes, 32, 0, s>>>(cand, tiles * K, K, in.W, scores, ys, xs, K, 0, nullptr);
+        return check_launch("peak_merge");
     }
-    if (rc != CL4_OK) return rc;
-    peak_merge_kernel<KPL><<<B * C, 32, 0, s>>>(cand, tiles * K, K, W, scores, ys, xs);
-    return check_launch("peak_merge");
+    unsigned long long* bound = cand + (size_t)planes * tiles * kPeakRound;
+    for (int done = 0; done < K; done += kPeakRound) {
+        const int k = K - done < kPeakRound ? K - done : kPeakRound;
+        peak_tile_kernel<KPL, Src><<<dim3(tiles, planes), kNmsThreads, smem, s>>>(in, r, k, tiles_x, tiles, done ? bound : nullptr, cand);
+        int rc = check_launch("peak_tile");
+        if (rc != CL4_OK) return rc;
+        peak_merge_kernel<KPL><<<planes, 32, 0, s>>>(cand, tiles * k, k, in.W, scores, ys, xs, K, done, bound);
+        rc = check_launch("peak_merge");
+        if (rc != CL4_OK) return rc;
+    }
+    return CL4_OK;
+}
+
+template <class Src>
+static int launch_peak_K(const PeakInput& in, float* scores, int* ys, int* xs, unsigned long long* cand, int planes, int r, int K,
+                         cudaStream_t s) {
+    if (K <= 32) return launch_peak<1, Src>(in, scores, ys, xs, cand, planes, r, K, s);
+    if (K <= 64) return launch_peak<2, Src>(in, scores, ys, xs, cand, planes, r, K, s);
+    if (K <= 128) return launch_peak<4, Src>(in, scores, ys, xs, cand, planes, r, K, s);
+    return launch_peak<8, Src>(in, scores, ys, xs, cand, planes, r, K, s);
 }
 
 template <int R>
@@ -734,28 +801,96 @@ extern "C" size_t cl4_peak_extract_scratch_bytes(int B, int C, int H, int W, int
     (void)kernel;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
     const size_t tiles = (size_t)cl4::ceil_div(W, cl4::kTileW) * cl4::ceil_div(H, cl4::kTileH);
-    return (size_t)B * C * tiles * K * sizeof(unsigned long long);
+    const size_t k = K < cl4::kPeakRound ? K : cl4::kPeakRound;  // candidates per tile and round; + one bound key per plane
+    return ((size_t)B * C * tiles * k + (size_t)B * C) * sizeof(unsigned long long);
 }
 
-extern "C" int cl4_peak_extract(const float* heat, float* scores, int* ys, int* xs, void* scratch, size_t scratch_bytes,
-                                int B, int C, int H, int W, int kernel, int K, cl4_stream_t stream) {
+static int peak_extract_checked(const cl4::PeakInput& in, float* scores, int* ys, int* xs, void* scratch, size_t scratch_bytes,
+                                int B, int C, int kernel, int K, cl4_stream_t stream) {
     using namespace cl4;
+    const int H = in.H, W = in.W;
     CL4_REQUIRE(B >= 0 && C >= 0 && H > 0 && W > 0, CL4_EINVAL, "peak_extract: bad shape");
     CL4_REQUIRE(kernel > 0 && (kernel & 1), CL4_EINVAL, "peak_extract: kernel must be odd and positive, got %d", kernel);
     CL4_REQUIRE(K >= 1 && (long long)K <= (long long)H * W, CL4_EINVAL, "peak_extract: K=%d out of range for %dx%d", K, H, W);
-    CL4_REQUIRE(K <= CL4_MAX_TOPK, CL4_EUNSUPPORTED, "peak_extract: K=%d > %d", K, CL4_MAX_TOPK);
     CL4_REQUIRE((long long)H * W < 0xffffffffll, CL4_EUNSUPPORTED, "peak_extract: plane too large");
     CL4_REQUIRE((long long)B * C <= 65535, CL4_EUNSUPPORTED, "peak_extract: B*C > 65535");
     if (B * C == 0) return CL4_OK;
-    CL4_REQUIRE(heat && scores && ys && xs, CL4_EINVAL, "peak_extract: null pointer");
+    CL4_REQUIRE(in.heat && scores && ys && xs, CL4_EINVAL, "peak_extract: null pointer");
     const int r = (kernel - 1) / 2;
     CL4_REQUIRE(nms_smem_bytes(r) <= 227 * 1024, CL4_EUNSUPPORTED, "peak_extract: kernel %d too large", kernel);
     CL4_REQUIRE(scratch && scratch_bytes >= cl4_peak_extract_scratch_bytes(B, C, H, W, kernel, K), CL4_ESCRATCH,
                 "peak_extract: scratch too small");
     unsigned long long* cand = reinterpret_cast<unsigned long long*>(scratch);
     cudaStream_t s = (cudaStream_t)stream;
-    if (K <= 32) return launch_peak<1>(heat, scores, ys, xs, cand, B, C, H, W, r, K, s);
-    if (K <= 64) return launch_peak<2>(heat, scores, ys, xs, cand, B, C, H, W, r, K, s);
-    if (K <= 128) return launch_peak<4>(heat, scores, ys, xs, cand, B, C, H, W, r, K, s);
-    return launch_peak<8>(heat, scores, ys, xs, cand, B, C, H, W, r, K, s);
+    if (in.h == 0) return launch_peak_K<PlaneSrc>(in, scores, ys, xs, cand, B * C, r, K, s);
+    return launch_peak_K<UpsampleSrc>(in, scores, ys, xs, cand, B * C, r, K, s);
+}
+
+extern "C" int cl4_peak_extract(const float* heat, float* scores, int* ys, int* xs, void* scratch, size_t scratch_bytes,
+                                int B, int C, int H, int W, int kernel, int K, cl4_stream_t stream) {
+    cl4::PeakInput in{heat, H, W, 0, 0, 0.f, 0.f};
+    return peak_extract_checked(in, scores, ys, xs, scratch, scratch_bytes, B, C, kernel, K, stream);
+}
+
+extern "C" int cl4_peak_extract_upsampled(const float* small, int h, int w, float* scores, int* ys, int* xs, void* scratch,
+                                          size_t scratch_bytes, int B, int C, int H, int W, int kernel, int K,
+                                          cl4_stream_t stream) {
+    CL4_REQUIRE(h > 0 && w > 0, CL4_EINVAL, "peak_extract_upsampled: bad source shape");
+    // ATen's area_pixel_compute_scale for align_corners = false without a user scale factor: float(in) / out
+    cl4::PeakInput in{small, H, W, h, w, H > 0 ? (float)h / (float)H : 0.f, W > 0 ? (float)w / (float)W : 0.f};
+    return peak_extract_checked(in, scores, ys, xs, scratch, scratch_bytes, B, C, kernel, K, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cam_normalize (reference wss/modules.py:425-434): relu, gating by the image-level labels, bilinear resize
+// (align_corners=False) to `size`, division by (plane maximum + 1e-5).  One CTA per (b, c) plane: pass 1 takes the maximum
+// of the resized plane, pass 2 writes the quotient (the resized values are recomputed: the source plane sits in L1).
+// ---------------------------------------------------------------------------------------------
+namespace cl4 {
+__global__ void __launch_bounds__(256)
+cam_normalize_kernel(const float* __restrict__ cam, const float* __restrict__ label, float* __restrict__ out, int h, int w,
+                     int hs, int ws, float sy, float sx) {
+    __shared__ float s_red[8];
+    const int plane = blockIdx.x;
+    const float* src = cam + (size_t)plane * h * w;
+    const float lab = label[plane];
+    const bool same = (h == hs && w == ws);  // the trainer's call (size = None): the resize is the identity
+    auto value = [&](int i) -> float {
+        auto tap = [&](int q) {  // F.relu keeps NaN (fmaxf would drop it), then the label gate
+            const float v = __ldg(src + q);
+            return __fmul_rn((v < 0.f) ? 0.f : v, lab);
+        };
+        if (same) return tap(i);
+        const int y = i / ws, x = i - y * ws;
+        const float fy = fmaxf(fmaf(sy, (float)y + 0.5f, -0.5f), 0.f), fx = fmaxf(fmaf(sx, (float)x + 0.5f, -0.5f), 0.f);
+        const int y1 = (int)fy, x1 = (int)fx;
+        const int yp = (y1 < h - 1) ? w : 0, xp = (x1 < w - 1) ? 1 : 0;
+        const float ly = fy - (float)y1, lx = fx - (float)x1, hy = 1.f - ly, hx = 1.f - lx;
+        const int q = y1 * w + x1;
+        return hy * (hx * tap(q) + lx * tap(q + xp)) + ly * (hx * tap(q + yp) + lx * tap(q + yp + xp));
+    };
+    const int n = hs * ws;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = nanmax(m, value(i));
+    for (int o = 16; o > 0; o >>= 1) m = nanmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = s_red[0];
+    for (int i = 1; i < 8; ++i) m = nanmax(m, s_red[i]);
+    const float denom = m + 1e-5f;  // F.adaptive_max_pool2d(cam, 1) + 1e-5
+    float* dst = out + (size_t)plane * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __fdiv_rn(value(i), denom);
+}
+}  // namespace cl4
+
+extern "C" int cl4_cam_normalize(const float* cam, const float* label, float* out, int B, int C, int h, int w, int hs, int ws,
+                                 cl4_stream_t stream) {
+    using namespace cl4;
+    CL4_REQUIRE(B >= 0 && C >= 0 && h > 0 && w > 0 && hs > 0 && ws > 0 && (long long)hs * ws < (1ll << 31), CL4_EINVAL,
+                "cam_normalize: bad shape");
+    if (B * C == 0) return CL4_OK;
+    CL4_REQUIRE(cam && label && out, CL4_EINVAL, "cam_normalize: null pointer");
+    cam_normalize_kernel<<<B * C, 256, 0, (cudaStream_t)stream>>>(cam, label, out, h, w, hs, ws, (float)h / (float)hs,
+                                                                  (float)w / (float)ws);
+    return check_launch("cam_normalize");
 }

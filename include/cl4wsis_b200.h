@@ -32,7 +32,6 @@ extern "C" {
 #define CL4_ESCRATCH (-4)     /* scratch buffer too small                              */
 
 #define CL4_MAX_DILATIONS 8
-#define CL4_MAX_TOPK 256
 
 typedef void* cl4_stream_t; /* cudaStream_t */
 typedef void* cl4_event_t;  /* cudaEvent_t  */
@@ -104,11 +103,26 @@ int cl4_pamr_forward_timed(const float* img, const float* mask_in, float* mask_o
  *   ys = int(float(idx)/W), xs = idx % W.
  * heat [B,C,H,W] -> scores f32 [B,C,K], ys i32 [B,C,K], xs i32 [B,C,K] (device).
  * kernel must be odd (an even kernel raises in the reference: shape mismatch at
- * wss/utils.py:11); 1 <= K <= min(H*W, CL4_MAX_TOPK).
+ * wss/utils.py:11); 1 <= K <= H*W (K > 256 is selected in rounds of 256).
  * ------------------------------------------------------------------------- */
 size_t cl4_peak_extract_scratch_bytes(int B, int C, int H, int W, int kernel, int K);
 int cl4_peak_extract(const float* heat, float* scores, int* ys, int* xs, void* scratch, size_t scratch_bytes,
                      int B, int C, int H, int W, int kernel, int K, cl4_stream_t stream);
+/* The phase-2 chain in front of peak_extract (train.py:426-436):
+ *   _, cam = peakgenerator(int_masks, l1h)   -> PeakGenerator.cam_normalize, wss/modules.py:425-434
+ *   cam = smoothing(cam)                     -> cl4_smoothing (wss/utils.py:28-32)
+ *   cam = F.interpolate(cam, images.shape[-2:], mode="bilinear", align_corners=False)
+ *   peak_extract(cam, kernel=15)
+ * cl4_cam_normalize: cam [B,C,h,w], label [B,C] -> out [B,C,hs,ws] = relu(cam) * label, bilinearly resized
+ *   (align_corners=False; hs == h and ws == w, the trainer's call, is the identity), divided by
+ *   (plane maximum + 1e-5).
+ * cl4_peak_extract_upsampled: peak_extract of F.interpolate(small [B,C,h,w], (H,W), bilinear,
+ *   align_corners=False) WITHOUT materialising the [B,C,H,W] map: the tile loader evaluates ATen's bilinear
+ *   formula on the fly from the small map.  Same outputs, scratch and limits as cl4_peak_extract(…, H, W, …). */
+int cl4_cam_normalize(const float* cam, const float* label, float* out, int B, int C, int h, int w, int hs, int ws,
+                      cl4_stream_t stream);
+int cl4_peak_extract_upsampled(const float* small, int h, int w, float* scores, int* ys, int* xs, void* scratch,
+                               size_t scratch_bytes, int B, int C, int H, int W, int kernel, int K, cl4_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
  * find_instance_center — modules/utils.py:463-502 (twin: dataset/utils.py:623-661),

@@ -46,7 +46,8 @@ def test_abi_version_and_scratch_queries(lib):
     assert n == 4 * 16 * 512 * 512 * 48 + 2 * 4 * 16 * 21 * 560 * 560 + 4 * 16 * 3 * 560 * 560
     assert lib.cl4_pamr_scratch_bytes(16, 3, 21, 512, 512, 6, 1) == 4 * 16 * 512 * 512 * 48 + 4 * 16 * (21 + 3) * 560 * 560
     assert lib.cl4_center_nms_scratch_bytes(1, 512, 512) >= 512 * 16 * 4 + 512 * 4
-    assert lib.cl4_peak_extract_scratch_bytes(2, 3, 64, 64, 15, 25) == 2 * 3 * 2 * 25 * 8
+    assert lib.cl4_peak_extract_scratch_bytes(2, 3, 64, 64, 15, 25) == (2 * 3 * 2 * 25 + 2 * 3) * 8  # candidates + one bound key per plane
+    assert lib.cl4_peak_extract_scratch_bytes(1, 1, 64, 64, 15, 1000) == (2 * 256 + 1) * 8     # K > 256: rounds of 256
 
 
 def test_argument_validation_returns_codes_without_a_gpu(lib):
@@ -60,7 +61,8 @@ def test_argument_validation_returns_codes_without_a_gpu(lib):
     assert lib.cl4_center_nms(null, 0.1, 0.0, 4, 1, 8, 8, null, null, 0, null, 0, null) == _lib.CL4_EINVAL
     assert b"odd" in lib.cl4_last_error()
     assert lib.cl4_peak_extract(null, null, null, null, null, 0, 1, 1, 8, 8, 3, 65, null) == _lib.CL4_EINVAL
-    assert lib.cl4_peak_extract(null, null, null, null, null, 0, 1, 1, 64, 64, 3, 300, null) == _lib.CL4_EUNSUPPORTED
+    assert lib.cl4_peak_extract(null, null, null, null, null, 0, 1, 1, 64, 64, 3, 300, null) == _lib.CL4_EINVAL  # K is fine; null pointers
+    assert b"null" in lib.cl4_last_error()
     assert lib.cl4_group_pixels(null, null, 1, 1, null, null, null, 1, 8, 8, 0, null) == _lib.CL4_EINVAL
     # misaligned buffers are refused before anything is launched (128-bit loads, TMA)
     v = ctypes.c_void_p

@@ -266,10 +266,65 @@ def test_peak_extract_errors(cl4):
         cl4.peak_extract(h, kernel=4, K=3)
     with pytest.raises(RuntimeError):
         cl4.peak_extract(h, kernel=3, K=65)
-    with pytest.raises(NotImplementedError):
-        cl4.peak_extract(torch.rand(1, 1, 32, 32, device="cuda"), kernel=3, K=300)
     with pytest.raises(RuntimeError):
         cl4.peak_extract(torch.rand(1, 1, 8, 8), kernel=3, K=3)
+
+
+@pytest.mark.parametrize("B,C,H,W,kernel,K", [(1, 2, 64, 96, 5, 300), (2, 1, 40, 40, 3, 1000), (1, 1, 33, 31, 15, 1023),
+                                              (1, 3, 128, 128, 41, 257)])
+def test_peak_extract_large_K(cl4, oracle, B, C, H, W, kernel, K):
+    """The reference accepts any K <= H*W (torch.topk, wss/utils.py:15); K > 256 is selected in rounds of 256."""
+    rng = np.random.default_rng(K)
+    heat = rng.random((B, C, H, W)).astype(np.float32)
+    heat[0, 0, :8] = np.round(heat[0, 0, :8] * 4) / 4        # plateaus: ties on the score
+    heat[0, 0, 20:24] = -heat[0, 0, 20:24]                    # negative peaks sort below the zeros
+    _check_peaks(cl4.peak_extract(cuda(heat), kernel=kernel, K=K), oracle.peak_extract(heat, kernel, K), heat)
+
+
+@pytest.mark.parametrize("name", ["cam_voc", "cam_odd", "cam_sized"])
+def test_cam_chain_golden(cl4, golden_more, oracle, name):
+    """train.py:426-436 (cam_normalize -> smoothing -> F.interpolate -> peak_extract) against reference outputs.  With
+    size = None (the trainer's call) cam_normalize is bit-exact; a real resize and the fused up-sampling inside the peak
+    loader agree to fp32 rounding (ATen's own CPU and CUDA kernels differ by as much), so the peak lists are compared
+    with tests/peaks_util.assert_peaks_equivalent: same pixels and scores except pixels that tie with their window
+    maximum to the last bits."""
+    from cl4wsis_b200.wss import utils as wu
+    from peaks_util import assert_peaks_equivalent
+    g = golden_more("cam")
+    k = name + "__"
+    cam, label = cuda(g[k + "cam"]), cuda(g[k + "label"])
+    size = tuple(int(v) for v in g[k + "size"])
+    norm = wu.cam_normalize(cam, size, label)
+    if size == tuple(cam.shape[-2:]):
+        assert np.array_equal(norm.cpu().numpy(), g[k + "norm"])
+        assert np.array_equal(wu.cam_normalize(cam, None, label).cpu().numpy(), g[k + "norm"])
+    else:
+        np.testing.assert_allclose(norm.cpu().numpy(), g[k + "norm"], rtol=2e-6, atol=1e-7)
+    kern, K = (int(v) for v in g[k + "kK"])
+    img = tuple(int(v) for v in g[k + "image_size"])
+    sc, ys, xs = (t.cpu().numpy() for t in wu.peak_extract_device(wu.smoothing(cuda(g[k + "norm"]), 3), kern, K, upsample_to=img))
+    up = oracle.labelgen.upsample_bilinear(g[k + "smooth"], img)
+    assert_peaks_equivalent((sc, ys, xs), (g[k + "scores"], g[k + "ys"], g[k + "xs"]), up, kern)
+    strong = g[k + "scores"] >= 0.25          # the peaks the trainer keeps have conf >= pseudo_thresh (train.py:456)
+    np.testing.assert_allclose(sc[strong], g[k + "scores"][strong], rtol=1e-5)
+    assert np.array_equal(ys[strong], g[k + "ys"][strong]) and np.array_equal(xs[strong], g[k + "xs"][strong])
+    if size == tuple(cam.shape[-2:]):  # the whole chain from the raw CAM in one call
+        sc2, ys2, xs2 = (t.cpu().numpy() for t in wu.cam_peaks(cam, label, img, 3, kern, K))
+        assert np.array_equal(sc2, sc) and np.array_equal(ys2, ys) and np.array_equal(xs2, xs)
+
+
+def test_peak_extract_upsampled_vs_materialised(cl4, fp32_convs):
+    """The trainer's shapes (B16, 20 classes, 32x32 -> 512x512, kernel 15, K 25): peaks of the on-the-fly up-sampling
+    against peak_extract of the map F.interpolate writes on this GPU."""
+    from cl4wsis_b200.wss import utils as wu
+    g = torch.Generator(device="cpu").manual_seed(31)
+    small = torch.rand((16, 20, 32, 32), generator=g).cuda()
+    small = wu.smoothing(small * (small > 0.5), 3)
+    up = torch.nn.functional.interpolate(small, size=(512, 512), mode="bilinear", align_corners=False)
+    ws, wy, wx = (t.cpu().numpy() for t in wu.peak_extract_device(up, 15, 25))
+    s, y, x = (t.cpu().numpy() for t in wu.peak_extract_device(small, 15, 25, upsample_to=(512, 512)))
+    from peaks_util import assert_peaks_equivalent
+    assert_peaks_equivalent((s, y, x), (ws, wy, wx), up.cpu().numpy(), 15)
 
 
 # --------------------------------------------------------------------------- find_instance_center

@@ -199,3 +199,23 @@ def test_get_ins_map_oracle_golden(golden_more, oracle, ci):
     assert pm.shape == shape and np.array_equal(pm, want)
     np.testing.assert_allclose(ps, g[k + "pred_score"], rtol=2e-6, atol=0)
     assert np.array_equal(off, g[k + "offset_after"][0])
+
+
+@pytest.mark.parametrize("name", ["cam_voc", "cam_odd", "cam_sized"])
+def test_cam_chain_oracle_golden(golden_more, oracle, name):
+    """oracle/labelgen.cam_normalize + upsample_bilinear against the reference's PeakGenerator.cam_normalize
+    (wss/modules.py:425-434), smoothing, F.interpolate(align_corners=False) and peak_extract (train.py:426-436)."""
+    g = golden_more("cam")
+    k = name + "__"
+    lg = oracle.labelgen
+    norm = lg.cam_normalize(g[k + "cam"], tuple(g[k + "size"]), g[k + "label"])
+    np.testing.assert_allclose(norm, g[k + "norm"], rtol=2e-6, atol=1e-7)
+    sm = lg.smoothing(g[k + "norm"], 3)
+    np.testing.assert_allclose(sm, g[k + "smooth"], rtol=2e-6, atol=1e-8)
+    H, W = (int(v) for v in g[k + "image_size"])
+    up = lg.upsample_bilinear(g[k + "smooth"], (H, W))
+    if k + "up" in g.files:
+        np.testing.assert_allclose(up, g[k + "up"], rtol=2e-6, atol=1e-7)
+    kern, K = (int(v) for v in g[k + "kK"])
+    from peaks_util import assert_peaks_equivalent
+    assert_peaks_equivalent(oracle.peak_extract(up, kern, K), (g[k + "scores"], g[k + "ys"], g[k + "xs"]), up, kern)
