@@ -224,6 +224,29 @@ center_flags_fast_kernel(const float* __restrict__ heat, float thr, float min_va
     int* s_col = smem_i + T::kPitch * T::kRows;
     const int n = blockIdx.z;
     const int y0 = blockIdx.y * kTileH, x0 = blockIdx.x * kTileW;
+    // Centres are sparse: a pixel can only be kept if its own value exceeds thr (a thresholded pixel reads -1, which is never
+    // > min_value when min_value >= -1).  A tile without such a pixel needs no halo and no max-pool: one coalesced pass over
+    // its own 2048 pixels, 64 zero words out.
+    if (min_value >= -1.f) {
+        const float* plane = heat + (size_t)n * H * W;
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < kTileH * kTileW / kNmsThreads; ++k) {
+            const int i = k * kNmsThreads + threadIdx.x;
+            const int y = y0 + i / kTileW, x = x0 + (i % kTileW);
+            if (y < H && x < W) {
+                const float v = __ldg(plane + (size_t)y * W + x);
+                any |= (v > thr) && (v > min_value);
+            }
+        }
+        if (!__syncthreads_or(any)) {
+            if (threadIdx.x < kTileH * (kTileW / 32)) {
+                const int y = y0 + threadIdx.x / (kTileW / 32), xw = (x0 >> 5) + threadIdx.x % (kTileW / 32);
+                if (y < H && xw < words_per_row) words[((size_t)n * H + y) * words_per_row + xw] = 0u;
+            }
+            return;
+        }
+    }
     T::template stage_and_columns<true>(PlaneSrc{heat + (size_t)n * H * W, W}, H, W, y0, x0, thr, s_key, s_col);
 
     // thread -> (row, 4-pixel group): lanes 0-15 one row, lanes 16-31 the next; two passes cover 32 rows
