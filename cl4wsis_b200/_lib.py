@@ -57,6 +57,9 @@ SIGNATURES = {
     "cl4_denorm": (_int, [_vp, _vp, _int, _int, ctypes.c_longlong, ctypes.POINTER(_flt), ctypes.POINTER(_flt), _vp]),
     "cl4_denorm_resize_ac": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _int, ctypes.POINTER(_flt),
                                     ctypes.POINTER(_flt), _vp]),
+    "cl4_phase1_scratch_bytes": (_sz, [_int] * 5),
+    "cl4_phase1_pseudo_labels": (_int, [_vp, _vp, _vp, ctypes.POINTER(_flt), ctypes.POINTER(_flt), ctypes.POINTER(_int), _int, _int,
+                                        _flt, _flt, _flt, _vp, _vp, _vp, _sz, _int, _int, _int, _int, _int, _int, _vp]),
     "cl4_softmax_channels": (_int, [_vp, _vp, _int, _int, ctypes.c_longlong, _vp]),
     "cl4_pseudo_gtmask": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _flt, _flt, _flt, _int, _vp]),
     "cl4_lattice_owner": (_int, [_int, _int, _int, ctypes.POINTER(_int), ctypes.POINTER(_int)]),

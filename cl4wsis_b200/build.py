@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcl4wsis_b200.so")
-SOURCES = ["core.cu", "group.cu", "nms.cu", "pamr.cu", "pamr_tma.cu", "pamr_lattice.cu", "pamr_duo.cu", "pamr_fused.cu", "ccl.cu", "stencil.cu", "refine.cu", "phase1.cu"]
+SOURCES = ["core.cu", "group.cu", "nms.cu", "pamr.cu", "pamr_tma.cu", "pamr_lattice.cu", "pamr_duo.cu", "pamr_fused.cu", "ccl.cu", "stencil.cu", "refine.cu", "phase1.cu", "phase1_fused.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall", "-I", os.path.join(ROOT, "include"), "-I", CSRC,

@@ -22,10 +22,26 @@ namespace cl4 {
 
 constexpr int kFusedMaxDim = 64;
 
-template <int D, class DS, int PITCH>
+// Phase-1 epilogue (kP1): what the trainer does with PAMR's result (train.py:382-385) happens on the values of the last
+// iteration while they are still in registers:
+//   int_masks_soft[:, 1:] *= l1h[:, :, None, None]      -> gated values go to `mask_out`
+//   pseudo_gtmask (wss/single_stage.py:18-40): plane maximum (NaN-propagating), x cutoff_bkg / cutoff_top, floored at
+//   cutoff_low -> thr[b, c]; pseudo = (mask > thr), pixels claimed by more than one class cleared.
+// The ambiguity rule couples all classes of a pixel, and the classes of an image are spread over several CTAs: every CTA
+// publishes its gated planes and thresholds, then takes a ticket from done[b]; the CTA that draws the last ticket of its image
+// writes the pseudo labels of the whole image (C x H x W <= 81 x 64 x 64 values, from L2).
+struct Phase1Epilogue {
+    const float* labels;  // [B, C-1] or nullptr
+    float* pseudo;        // [B, C, H, W]
+    float* thr;           // [B, C]
+    int* done;            // [B], zeroed by the prologue kernel
+    float cutoff_top, cutoff_bkg, cutoff_low;
+};
+
+template <int D, class DS, int PITCH, bool kP1>
 __global__ void __launch_bounds__(kSweepThreads, 1)
 pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_in, float* __restrict__ mask_out,
-                  int C, int H, int W, int cpb, int num_iter, Dilations dil) {
+                  int C, int H, int W, int cpb, int num_iter, Dilations dil, Phase1Epilogue ep) {
     constexpr int P = 8 * D;
     constexpr int kPlane = PITCH * PITCH;  // PITCH rows of PITCH floats
     extern __shared__ __align__(16) float smem[];
@@ -75,6 +91,12 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
     }
     __syncthreads();
 
+    constexpr int kCpbCap = (227 * 1024) / (2 * kPlane * 4);   // classes per CTA that fit (launch_fused_one)
+    __shared__ float s_cmax[kP1 ? kCpbCap * (kSweepThreads / 32) : 1];  // running plane maxima, one slot per (class, warp)
+    __shared__ int s_last;
+    if (kP1)
+        for (int i = tid; i < kCpbCap * (kSweepThreads / 32); i += kSweepThreads) s_cmax[i] = -INFINITY;
+
     float acc[kPx];
     for (int it = 0; it < num_iter; ++it) {
         const int cur = it & 1, nxt = cur ^ 1;
@@ -99,6 +121,19 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
                     sweep_class<D, DS, false, PITCH>(w, sp, dil, nullptr, acc);
                 if (last_it) {
                     float* o = mask_out + ((size_t)b * C + c0 + c) * HW + (size_t)(y0 + ty) * W + x;
+                    if (kP1) {
+                        const int cls = c0 + c;
+                        const float g = (ep.labels && cls > 0) ? __ldg(ep.labels + (size_t)b * (C - 1) + (cls - 1)) : 1.f;
+                        float m = -INFINITY;
+#pragma unroll
+                        for (int i = 0; i < kPx; ++i) {
+                            if (ep.labels && cls > 0) acc[i] = __fmul_rn(acc[i], g);
+                            if ((valid >> i) & 1u) m = nanmax(m, acc[i]);  // torch.max propagates NaN
+                        }
+#pragma unroll
+                        for (int sft = 16; sft > 0; sft >>= 1) m = nanmax(m, __shfl_xor_sync(0xffffffffu, m, sft));
+                        if (lane == 0) s_cmax[c * (kSweepThreads / 32) + wrp] = nanmax(s_cmax[c * (kSweepThreads / 32) + wrp], m);
+                    }
 #pragma unroll
                     for (int i = 0; i < kPx; ++i)
                         if ((valid >> i) & 1u) o[(size_t)(i * kRowGap) * W] = acc[i];
@@ -135,6 +170,34 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
         }
         __syncthreads();
     }
+
+    if (kP1) {
+        __syncthreads();  // s_cmax complete; this CTA's gated planes are on their way to L2
+        if (tid < nc) {
+            float mx = s_cmax[tid * (kSweepThreads / 32)];
+            for (int wi = 1; wi < kSweepThreads / 32; ++wi) mx = nanmax(mx, s_cmax[tid * (kSweepThreads / 32) + wi]);
+            const int cls = c0 + tid;
+            const float scaled = __fmul_rn(mx, cls == 0 ? ep.cutoff_bkg : ep.cutoff_top);  // mask_max[:, :1] *= bkg; [:, 1:] *= top
+            ep.thr[(size_t)b * C + cls] = (ep.cutoff_low > scaled || ep.cutoff_low != ep.cutoff_low) ? ep.cutoff_low : scaled;
+        }
+        __threadfence();  // every thread: its stores to mask_out / thr are visible device-wide before the ticket is drawn
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(ep.done + b, 1) == (int)gridDim.x - 1);
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const float* gm = mask_out + (size_t)b * C * HW;
+            const float* th = ep.thr + (size_t)b * C;
+            float* po = ep.pseudo + (size_t)b * C * HW;
+            for (int i = tid; i < (int)HW; i += kSweepThreads) {
+                int n = 0;
+                for (int c = 0; c < C; ++c) n += (__ldcg(gm + (size_t)c * HW + i) > __ldcg(th + c));
+                const bool clear = n > 1;  // ambiguous=True (train.py:384)
+                for (int c = 0; c < C; ++c)
+                    po[(size_t)c * HW + i] = (!clear && __ldcg(gm + (size_t)c * HW + i) > __ldcg(th + c)) ? 1.f : 0.f;
+            }
+        }
+    }
 }
 
 bool pamr_fused_applicable(int H, int W, const Dilations& dil, int D) {
@@ -159,10 +222,24 @@ static int pick_cpb(int B, int C, int cpb_max) {
     return best;
 }
 
+// set by launch_pamr_fused_phase1 around the dispatch below (same host thread)
+static thread_local const Phase1Epilogue* t_ep = nullptr;
+
+template <int D, class DS, int PITCH, bool kP1>
+static int launch_fused_one_ep(const float* w, const float* mi, float* mo, int B, int C, int H, int W, int num_iter,
+                               const Dilations& dil, cudaStream_t s);
+
 template <int D, class DS, int PITCH>
 static int launch_fused_one(const float* w, const float* mi, float* mo, int B, int C, int H, int W, int num_iter,
                             const Dilations& dil, cudaStream_t s) {
-    auto kern = pamr_fused_kernel<D, DS, PITCH>;
+    if (t_ep) return launch_fused_one_ep<D, DS, PITCH, true>(w, mi, mo, B, C, H, W, num_iter, dil, s);
+    return launch_fused_one_ep<D, DS, PITCH, false>(w, mi, mo, B, C, H, W, num_iter, dil, s);
+}
+
+template <int D, class DS, int PITCH, bool kP1>
+static int launch_fused_one_ep(const float* w, const float* mi, float* mo, int B, int C, int H, int W, int num_iter,
+                               const Dilations& dil, cudaStream_t s) {
+    auto kern = pamr_fused_kernel<D, DS, PITCH, kP1>;
     constexpr size_t kPlaneBytes = (size_t)PITCH * PITCH * 4;
     constexpr int kCpbMax = (int)((227 * 1024) / (2 * kPlaneBytes));
     static_assert(kCpbMax >= 1, "plane too large for shared memory");
@@ -174,7 +251,7 @@ static int launch_fused_one(const float* w, const float* mi, float* mo, int B, i
         return CL4_ECUDA;
     }
     dim3 grid(ceil_div(C, cpb), B);
-    kern<<<grid, kSweepThreads, smem, s>>>(w, mi, mo, C, H, W, cpb, num_iter, dil);
+    kern<<<grid, kSweepThreads, smem, s>>>(w, mi, mo, C, H, W, cpb, num_iter, dil, kP1 ? *t_ep : Phase1Epilogue{});
     return check_launch("pamr_fused");
 }
 
@@ -211,6 +288,17 @@ int launch_pamr_fused(const float* w, const float* mask_in, float* mask_out, int
                       const Dilations& dil, int D, cudaStream_t s) {
     if (H <= kTile && W <= kTile) return launch_fused_P<kBox>(w, mask_in, mask_out, B, C, H, W, num_iter, dil, D, s);
     return launch_fused_P<2 * kTile + 2 * kHalo>(w, mask_in, mask_out, B, C, H, W, num_iter, dil, D, s);
+}
+
+// The same launch with the phase-1 epilogue: mask_out receives the label-gated masks, pseudo / thr as Phase1Epilogue says.
+int launch_pamr_fused_phase1(const float* w, const float* mask_in, float* gated_out, float* pseudo_out, float* thr, int* done,
+                             const float* labels, float cutoff_top, float cutoff_bkg, float cutoff_low, int B, int C, int H, int W,
+                             int num_iter, const Dilations& dil, int D, cudaStream_t s) {
+    Phase1Epilogue ep{labels, pseudo_out, thr, done, cutoff_top, cutoff_bkg, cutoff_low};
+    t_ep = &ep;
+    const int rc = launch_pamr_fused(w, mask_in, gated_out, B, C, H, W, num_iter, dil, D, s);
+    t_ep = nullptr;
+    return rc;
 }
 
 }  // namespace cl4

@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "pamr_internal.cuh"
 #include "pamr_sweep.cuh"
+#include "pamr_weights.cuh"
 #include "tma.cuh"
 
 namespace cl4 {
@@ -318,61 +319,15 @@ pamr_weights_tma_kernel(const __grid_constant__ CUtensorMap tmap, float* __restr
     mbar_wait(bar, 0);
 
     float4* o = reinterpret_cast<float4*>(wts) + (size_t)blockIdx.x * (P / 4 * kTile * kTile) + lane;
-    const float invK = 1.f / (float)K;
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {
         const int row = wrp + 8 * i;
         const float* sp0 = win + (row + kHalo) * kBox + lane + kHalo;
         float logit[P];
-#pragma unroll
-        for (int p = 0; p < P; ++p) logit[p] = 0.f;
-#pragma unroll 1
-        for (int k = 0; k < K; ++k) {
-            const float* sp = sp0 + k * (kBox * kBox);
-            const float c = sp[0];
-            float dlt[P];  // neighbour - centre; the D centre samples of LocalStDev contribute zeros
-#pragma unroll
-            for (int di = 0; di < D; ++di) {
-                const int d = DS::kStatic ? DS::get(di) : dil.d[di];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int dy = (j < 3) ? -1 : ((j < 5) ? 0 : 1);
-                    const int dx = (j < 3) ? (j - 1) : ((j == 3) ? -1 : ((j == 4) ? 1 : (j - 6)));
-                    dlt[di * 8 + j] = sp[dy * d * kBox + dx * d] - c;
-                }
-            }
-            float s1 = 0.f;
-#pragma unroll
-            for (int p = 0; p < P; ++p) s1 += dlt[p];
-            const float mean = s1 * (1.f / (float)(9 * D));
-            float ss = (float)D * mean * mean;
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                const float t = dlt[p] - mean;
-                ss = fmaf(t, t, ss);
-            }
-            const float sd = sqrtf(ss * (1.f / (float)(9 * D - 1)));
-            const float ninv = -1.f / (1e-8f + 0.1f * sd);
-#pragma unroll
-            for (int p = 0; p < P; ++p) logit[p] = fmaf(fabsf(dlt[p]), ninv, logit[p]);
-        }
-        float mx = -INFINITY;
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            logit[p] *= invK;
-            mx = fmaxf(mx, logit[p]);
-        }
-        float z = 0.f;
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            logit[p] = __expf(logit[p] - mx);
-            z += logit[p];
-        }
-        const float rz = 1.f / z;
+        pixel_affinity<D, DS>(sp0, K, kBox * kBox, kBox, dil, logit);
 #pragma unroll
         for (int g = 0; g < P / 4; ++g)
-            o[(size_t)g * (kTile * kTile) + row * kTile] =
-                make_float4(logit[4 * g] * rz, logit[4 * g + 1] * rz, logit[4 * g + 2] * rz, logit[4 * g + 3] * rz);
+            o[(size_t)g * (kTile * kTile) + row * kTile] = make_float4(logit[4 * g], logit[4 * g + 1], logit[4 * g + 2], logit[4 * g + 3]);
     }
 }
 

@@ -64,7 +64,7 @@ __global__ void softmax_channels_kernel(const float* __restrict__ in, float* __r
 // One CTA per (b, c) plane: gate the fg planes by the image-level label (train.py:382), keep the plane
 // maximum and turn it into the plane's threshold (wss/single_stage.py:24-32).
 __global__ void __launch_bounds__(256)
-gate_and_threshold_kernel(const float* __restrict__ mask, const float* __restrict__ labels, float* __restrict__ gated, int C,
+gate_and_threshold_kernel(const float* mask, const float* __restrict__ labels, float* gated, int C,  // gated may alias mask
                           int HW, float cutoff_top, float cutoff_bkg, float cutoff_low, float* __restrict__ thr) {
     __shared__ float s_max[8];
     const int c = blockIdx.x, b = blockIdx.y;

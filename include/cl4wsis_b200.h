@@ -257,6 +257,18 @@ int cl4_ins_masks(const int* inst_map, int n, int H, int W, unsigned char* masks
  *   cutoff_low; pseudo_out = (mask > threshold) as 0/1 floats, pixels claimed by more than one class cleared
  *   when `ambiguous`.  thr_scratch: B*C floats.
  * ------------------------------------------------------------------------- */
+/* The whole of train.py:372-385 for feature-resolution maps (h, w <= 64; 1..6 dilations, each <= 24; num_iter >= 1) in TWO
+ * launches: (1) per (image, 32x32 tile): denorm + align-corners shrink of the image into a shared-memory window, affinity
+ * weights from it, class softmax; (2) all num_iter PAMR sweeps on-chip followed by label gating, plane maxima, thresholds
+ * and pseudo_gtmask(ambiguous=True) -- the last CTA of an image to finish writes its pseudo labels.
+ * images [B,3,Hi,Wi], int_masks [B,C,h,w] logits, l1h [B,C-1] or NULL, mean / std: HOST arrays of three floats (NULL: no
+ * denorm) -> soft_out [B,C,h,w] (int_masks_soft after gating), pseudo_out [B,C,h,w] (0/1).  CL4_EUNSUPPORTED outside the
+ * stated range: use the separate entry points above. */
+size_t cl4_phase1_scratch_bytes(int B, int C, int h, int w, int D);
+int cl4_phase1_pseudo_labels(const float* images, const float* int_masks, const float* l1h, const float* mean,
+                             const float* std, const int* dilations, int D, int num_iter, float cutoff_top,
+                             float cutoff_bkg, float cutoff_low, float* soft_out, float* pseudo_out, void* scratch,
+                             size_t scratch_bytes, int B, int C, int Hi, int Wi, int h, int w, cl4_stream_t stream);
 int cl4_denorm(const float* images, float* out, int planes, int K, long long HW, const float* mean, const float* std,
                cl4_stream_t stream);
 int cl4_denorm_resize_ac(const float* images, float* out, int B, int K, int Hi, int Wi, int h, int w, const float* mean,

@@ -743,7 +743,7 @@ def test_phase1_pieces_match_reference(cl4, golden_more, name):
     assert np.array_equal(pseudo.cpu().numpy(), k("pseudo"))
 
 
-@pytest.mark.parametrize("name", ["p1_rect", "p1_voc"])
+@pytest.mark.parametrize("name", ["p1_one", "p1_rect", "p1_same", "p1_voc"])
 def test_phase1_fused_step(cl4, golden_more, name):
     """The whole of train.py:372-385 through phase1_pseudo_labels (softmax, denorm + shrink, PAMR with the trainer's
     five dilations, gating, pseudo_gtmask).  The refined masks match to PAMR's tolerance; a pseudo-label may only
@@ -762,6 +762,34 @@ def test_phase1_fused_step(cl4, golden_more, name):
     near_px = near.any(axis=1, keepdims=True)  # the ambiguity rule couples the classes of a pixel
     diff = pseudo.cpu().numpy() != k("pseudo")
     assert not (diff & ~near_px).any(), int((diff & ~near_px).sum())
+
+
+@pytest.mark.parametrize("B,C,h,w,Hi,Wi,dil", [
+    (16, 21, 32, 32, 512, 512, [1, 2, 4, 8, 12]),      # the VOC trainer's shapes: 7 CTAs per image share the ambiguity rule
+    (4, 81, 56, 56, 448, 448, [1, 2, 4, 8, 12]),       # coco-voc: 2 x 2 tiles, 41 CTAs per image
+    (3, 5, 19, 26, 75, 102, [1, 2, 4, 8, 12, 24]),     # odd sizes, six dilations
+    (2, 2, 64, 64, 64, 64, [1, 3]),                    # shrink factor 1, runtime dilation set
+])
+def test_phase1_two_launch_path_equals_separate_kernels(cl4, B, C, h, w, Hi, Wi, dil):
+    """cl4_phase1_pseudo_labels (2 launches: prologue + on-chip PAMR with the gating / pseudo_gtmask epilogue) against the
+    same step run as separate kernels (train.py:372-385): identical pseudo labels, soft masks equal to rounding."""
+    from cl4wsis_b200.wss import single_stage as ss
+    g = torch.Generator(device="cpu").manual_seed(B * 100 + C)
+    images = ((torch.rand((B, 3, Hi, Wi), generator=g) - 0.45) / 0.226).cuda()
+    logits = (3 * torch.randn((B, C, h, w), generator=g)).cuda()
+    l1h = (torch.rand((B, C - 1), generator=g) < 0.4).float().cuda()
+    l1h[:, 0] = 1
+    mod = cl4.PAMR(10, dil).cuda()
+    assert ss._fused_applicable(mod, h, w) and ss.PHASE1_LAUNCHES == 2
+    soft, pseudo = ss.phase1_pseudo_labels(images, logits, l1h, mod)
+    soft_u, pseudo_u = ss.phase1_pseudo_labels_unfused(images, logits, l1h, mod)
+    torch.testing.assert_close(soft, soft_u, rtol=1e-6, atol=1e-8)
+    if torch.equal(soft, soft_u):
+        assert torch.equal(pseudo, pseudo_u)
+    else:  # a pseudo label may only differ where the mask sits within rounding of its threshold
+        assert (pseudo != pseudo_u).float().mean().item() < 1e-4
+    assert pseudo.sum(1).max().item() <= 1.0           # ambiguous pixels are cleared across ALL classes of an image
+    assert 0 < pseudo.sum().item() < pseudo.numel()
 
 
 def test_phase1_error_behaviour(cl4):
