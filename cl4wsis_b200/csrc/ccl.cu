@@ -4,7 +4,7 @@
 //   cv2.connectedComponentsWithStats(weak, connectivity=4)   -> area and centroid per component
 // Union-find over pixels (atomicMin on parent links); a component is represented by its smallest
 // pixel index, which is also OpenCV's label order for 4-connectivity (labels are numbered by the
-// first pixel met in raster order — pinned against cv2 in tests/test_cluster.py).
+// first pixel met in raster order — pinned against cv2 in tests/test_gpu_parity.py::test_cluster_peaks_matches_opencv).
 #include "ccl.cuh"
 #include "common.cuh"
 

@@ -800,9 +800,9 @@ extern "C" int cl4_center_nms(const float* heat, float threshold, float min_valu
     const int r = (kernel - 1) / 2;
     const size_t smem = nms_smem_bytes(r);
     CL4_REQUIRE(smem <= 227 * 1024, CL4_EUNSUPPORTED, "center_nms: nms kernel %d too large for the tile", kernel);
+    if (N == 0) return CL4_OK;  // an empty batch needs no scratch (as every other entry point)
     CL4_REQUIRE(scratch && scratch_bytes >= cl4_center_nms_scratch_bytes(N, H, W), CL4_ESCRATCH,
                 "center_nms: scratch too small");
-    if (N == 0) return CL4_OK;
     const int wpr = ceil_div(W, 32);
     uint32_t* words = reinterpret_cast<uint32_t*>(scratch);
     int* row_off = reinterpret_cast<int*>(reinterpret_cast<char*>(scratch) +

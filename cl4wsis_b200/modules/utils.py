@@ -205,7 +205,8 @@ def refine_label_generation_device(seg_map, center_map, offset_map, label, gt_se
 
 def contours8(gt_seg_map, label, min_area=MINIMUM_MASK_SIZE):
     """8-connected contours of every valid (image, class) on the GPU (``cl4_contours8``):
-    -> (comp [B,H,W] int32 slot map, info [B,n_max,5] int32 (first pixel, cls, cx, cy, area), ncomp [B])."""
+    -> (comp [B,H,W] int32 slot map, info [B,n_max,5] int32 (first pixel, cls, cx, cy, area), ncomp [B]).
+    Hard limit: ``cl4_refine_max_contours()`` (1024) contours of >= ``min_area`` px per image, ``NotImplementedError`` beyond."""
     lib = _lib.load()
     _lib.require_cuda(gt_seg_map, "gt_seg_map")
     dev = gt_seg_map.device
@@ -232,8 +233,10 @@ def contours8(gt_seg_map, label, min_area=MINIMUM_MASK_SIZE):
 
 def refine_label_generation_per_contour(seg_map, center_map, offset_map, label, gt_seg_map, top_k, args):
     """The reference's loop structure (image x contour x instance, modules/utils.py:295-377) on this
-    package's kernels: exact for every input, at the reference's cost of several host round trips per
-    contour.  Used when the batched path reports a capacity overflow."""
+    package's kernels, at the reference's cost of several host round trips per contour.  Used when the batched
+    path reports a capacity overflow.  Exact for every input with at most ``cl4_refine_max_contours()`` (1024)
+    contours of >= 20 px per image; beyond that ``contours8`` raises ``NotImplementedError`` (OpenCV, which the
+    reference uses, has no such limit -- a 512 x 512 label map would need a contour every 256 px to get there)."""
     seg, ctr, off, lab, gt = _refine_inputs(seg_map, center_map, offset_map, label, gt_seg_map)
     B, C, H, W = ctr.shape
     dev = ctr.device
@@ -294,7 +297,8 @@ def refine_label_generation(seg_map, center_map, offset_map, label, gt_seg_map, 
 
     Runs the whole batch on the device with ONE host synchronisation (the status word); the
     reference needs >= 6 per contour.  Inputs that exceed a capacity limit of the
-    batched path (status != 0) are recomputed by the exact per-contour path.
+    batched path (status != 0) are recomputed by the per-contour path (which shares the hard limit of 1024
+    contours of >= 20 px per image and raises ``NotImplementedError`` beyond it).
     """
     out, status = refine_label_generation_device(seg_map, center_map, offset_map, label, gt_seg_map, top_k, args)
     if int(status.item()) != 0:

@@ -13,7 +13,14 @@ from . import _lib
 
 
 class PseudoLabelStep:
-    """Pre-allocated workspace + launches for a fixed (B, C, H, W) batch shape on one GPU."""
+    """Pre-allocated workspace + launches for a fixed (B, C, H, W) batch shape on one GPU.
+
+    Capacity: ``cl4_center_nms`` stores the first ``max_centers`` centres of an image (``counts`` holds the true total) and
+    the grouping uses the stored ones, so an image with more centres than ``max_centers`` is grouped against a truncated list
+    -- unlike the reference's ``find_instance_center`` + ``group_pixels``.  Nothing is synchronised inside ``run``; check
+    ``overflowed()`` (a device tensor, no sync) or ``assert_no_overflow()`` (one sync) and re-run such images through the
+    drop-in functions of ``cl4wsis_b200.modules.utils``, or size ``max_centers`` for the worst case
+    (``H * W / nms_kernel**2`` bounds the number of strict maxima; plateaux can exceed it)."""
 
     def __init__(self, B, C, H, W, K=3, num_iter=10, dilations=(1, 2, 4, 8, 12, 24), threshold=0.3, nms_kernel=41,
                  max_centers=256, ignore=True, device=None):
@@ -71,6 +78,17 @@ class PseudoLabelStep:
                                         _lib.ptr(offsets), _lib.ptr(fg), _lib.ptr(self.ids), B, H, W,
                                         self.empty_mode, st), "group_pixels")
         return self.refined, self.ids, self.counts, self.centers
+
+    def overflowed(self):
+        """[B] bool device tensor: images of the last ``run`` whose centre list was truncated to ``max_centers``."""
+        return self.counts > self.max_centers
+
+    def assert_no_overflow(self):
+        """One host sync: raises if any image of the last ``run`` had more than ``max_centers`` centres."""
+        bad = torch.nonzero(self.overflowed()).flatten().tolist()
+        if bad:
+            raise OverflowError(f"PseudoLabelStep: images {bad} have more than max_centers={self.max_centers} centres; their "
+                                "instance ids were computed against a truncated centre list")
 
 
 class HostPseudoLabelPipeline:

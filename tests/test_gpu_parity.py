@@ -460,6 +460,29 @@ def test_pseudo_label_step_matches_per_image_oracle(cl4, oracle):
             assert int(ids[b].abs().sum()) == 0  # ignore=True: zeros (modules/utils.py:597-598)
         else:
             assert np.array_equal(ids[b].cpu().numpy(), oracle.group_pixels(ctr, off[b:b + 1])[0])
+    assert not bool(step.overflowed().any())
+    step.assert_no_overflow()
+
+
+def test_pseudo_label_step_reports_truncated_centre_lists(cl4, oracle):
+    """More centres than max_centers: counts keeps the true total, the stored list is the first max_centers in nonzero
+    order, and the overflow is reported instead of passing silently."""
+    rng = np.random.default_rng(7)
+    B, C, H, W = 2, 2, 64, 64
+    x = rng.random((B, 3, H, W)).astype(np.float32)
+    m = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).softmax(1).numpy()
+    heat = np.zeros((B, 1, H, W), np.float32)
+    heat[1, 0, 4::8, 4::8] = rng.uniform(0.5, 1.0, (8, 8)).astype(np.float32)  # 64 isolated maxima at k = 3
+    heat[0, 0, 10, 10] = 0.9
+    off = np.zeros((B, 2, H, W), np.float32)
+    step = cl4.PseudoLabelStep(B, C, H, W, num_iter=1, threshold=0.3, nms_kernel=3, max_centers=16)
+    _, _, counts, centers = step.run(cuda(x), cuda(m), cuda(heat), cuda(off))
+    assert counts.tolist() == [1, 64]
+    assert step.overflowed().tolist() == [False, True]
+    ctr = oracle.find_instance_center(heat[1:2], 0.3, 3)
+    assert np.array_equal(centers[1].cpu().numpy(), ctr[:16])
+    with pytest.raises(OverflowError):
+        step.assert_no_overflow()
 
 
 # --------------------------------------------------------------------------- refine_label_generation
