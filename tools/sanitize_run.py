@@ -54,5 +54,22 @@ mu.pseudo_label_generation_batch(gt, pk, lab, 0.7, 6)
 step = cl4.PseudoLabelStep(2, 4, 64, 96, num_iter=3, dilations=[1, 2, 4, 8, 12, 24], threshold=0.3, nms_kernel=41, max_centers=32)
 step.run(torch.rand(2, 3, 64, 96, device=dev), torch.rand(2, 4, 64, 96, device=dev).softmax(1), torch.rand(2, 1, 64, 96, device=dev),
          torch.randn(2, 2, 64, 96, device=dev))
+# round-2 paths: class-pair sweep with an odd class count and partial tiles, K > 256, the phase-2 CAM chain with the
+# up-sampling inside the tile loader, get_ins_map on the device
+cl4.PAMR(3, [1, 2, 4, 8, 12, 24]).cuda()(torch.rand(1, 3, 100, 132, device=dev), torch.rand(1, 5, 100, 132, device=dev).softmax(1))
+peak_extract_device(heat, 5, 300)
+from cl4wsis_b200.wss.utils import cam_peaks
+cam_peaks(torch.randn(2, 3, 20, 24, device=dev), torch.ones(2, 3, device=dev), (70, 90))
+from cl4wsis_b200.dataset.utils import get_ins_map
+
+
+class V:
+    val_flip, val_clean, val_thresh, val_kernel, beta, val_ignore = True, True, 0.3, 41, 3.0, True
+
+
+seg = torch.randn(2, C + 1, H, W, device=dev)
+seg[:, 1, 10:60, 10:50] += 6
+seg[:, 2, 20:65, 55:85] += 6
+get_ins_map({'seg': seg, 'center': heat[:2].contiguous(), 'offset': torch.randn(2, 2, H, W, device=dev)}, torch.ones(1, C), (H, W), dev, V)
 torch.cuda.synchronize()
 print("sanitize_run ok, status", int(st.item()))
