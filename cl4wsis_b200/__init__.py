@@ -8,10 +8,14 @@ Drop-in mirrors of the reference API for this path (same names and signatures):
     cl4wsis_b200.modules.utils.group_pixels                modules/utils.py:505-542
     cl4wsis_b200.modules.utils.get_instance_segmentation   modules/utils.py:545-606
     cl4wsis_b200.modules.utils.refine_label_generation     modules/utils.py:257-385
+    cl4wsis_b200.modules.utils.refine_label_generation_with_point   modules/utils.py:388-460
+    cl4wsis_b200.dataset.utils.get_ins_map                 dataset/utils.py:795-902
+    cl4wsis_b200.wss.single_stage.phase1_pseudo_labels     train.py:372-385 (+ pseudo_gtmask, wss/single_stage.py:18-40)
+    cl4wsis_b200.wss.utils.cam_peaks / cam_normalize / smoothing   train.py:426-436, wss/modules.py:425-434
     cl4wsis_b200.wss.modules.LocalAffinity[Abs|Copy], LocalStDev   wss/modules.py:17-119
 
 All compute happens in hand-written CUDA kernels behind the C ABI in
-``include/cl4wsis_b200.h`` (``libcl4wsis_b200.so``); there is no CPU or PyTorch fallback.
+``include/cl4wsis_b200.h`` (``libcl4wsis_b200.so``); there is no CPU fallback.
 """
 from . import _lib  # noqa: F401
 from .wss.modules import PAMR  # noqa: F401
@@ -40,3 +44,4 @@ def patch_reference(wss_modules=None, wss_utils=None, modules_utils=None):
         modules_utils.group_pixels = mu.group_pixels
         modules_utils.get_instance_segmentation = mu.get_instance_segmentation
         modules_utils.refine_label_generation = mu.refine_label_generation
+        modules_utils.refine_label_generation_with_point = mu.refine_label_generation_with_point

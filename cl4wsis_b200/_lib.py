@@ -49,6 +49,7 @@ SIGNATURES = {
     "cl4_contours8": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cl4_refine_labels": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, ctypes.c_double, _int, _flt, _int, _int,
                                  ctypes.c_longlong, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _sz, _vp]),
+    "cl4_refine_labels_with_point": (_int, [_vp] * 7 + [_int] * 5 + [_vp]),
     "cl4_ins_map_max_instances": (_int, []),
     "cl4_ins_map_scratch_bytes": (_sz, [_int] * 3),
     "cl4_ins_map": (_int, [_vp, _vp, _vp, _vp, _int, _flt, _flt, _flt, _int, _flt, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp,

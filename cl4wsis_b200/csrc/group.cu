@@ -137,7 +137,68 @@ group_pixels_kernel(const long long* __restrict__ ctr, const int* __restrict__ c
     }
 }
 
+// refine_label_generation_with_point (reference modules/utils.py:388-460): one thread per pixel.  The pixel's class is its
+// gt label - 1; its centres are that class's kept points (the reference drops points with y == 0 or x == 0, :436), the
+// nearest one by group_pixels' arithmetic (first minimum) gives the offset (:458-459), every such pixel gets weight 1.
+// Pixels of invalid classes (:431) or of classes without a kept point (:439) stay zero.
+__global__ void __launch_bounds__(256)
+refine_with_point_kernel(const long long* __restrict__ gt, const float* __restrict__ label, const long long* __restrict__ pts,
+                         const unsigned char* __restrict__ keep, const float* __restrict__ offsets, float* __restrict__ out_off,
+                         float* __restrict__ out_w, int C, int M, int H, int W) {
+    const int b = blockIdx.y, HW = H * W;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= HW) return;
+    float oy = 0.f, ox = 0.f, wgt = 0.f;
+    const long long g = gt[(size_t)b * HW + i];
+    if (g >= 1 && g <= C && label[(size_t)b * C + (g - 1)] != 0.f) {
+        const int cls = (int)g - 1;
+        const long long* p = pts + ((size_t)b * C + cls) * M * 2;
+        const unsigned char* kp = keep + ((size_t)b * C + cls) * M;
+        const int y = i / W, x = i - y * W;
+        const float ly = __fadd_rn((float)y, offsets[(size_t)b * 2 * HW + i]);
+        const float lx = __fadd_rn((float)x, offsets[((size_t)b * 2 + 1) * HW + i]);
+        float best = 0.f, by = 0.f, bx = 0.f;
+        bool any = false;
+        for (int m = 0; m < M; ++m) {
+            if (!kp[m]) continue;
+            const float cy = (float)p[2 * m], cx = (float)p[2 * m + 1];
+            const float dy = __fsub_rn(cy, ly), dx = __fsub_rn(cx, lx);
+            const float d = __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+            if (!any || d < best) {  // first minimum wins (and a NaN distance never replaces the first point)
+                best = d;
+                by = cy;
+                bx = cx;
+                any = true;
+            }
+        }
+        if (any) {
+            oy = __fsub_rn(by, (float)y);
+            ox = __fsub_rn(bx, (float)x);
+            wgt = 1.f;
+        }
+    }
+    out_off[(size_t)b * 2 * HW + i] = oy;
+    out_off[((size_t)b * 2 + 1) * HW + i] = ox;
+    out_w[(size_t)b * HW + i] = wgt;
+}
+
 }  // namespace cl4
+
+extern "C" int cl4_refine_labels_with_point(const long long* gt_seg, const float* label, const long long* points,
+                                            const unsigned char* keep, const float* offsets, float* out_offset,
+                                            float* out_weight, int B, int C, int M, int H, int W, cl4_stream_t stream) {
+    using namespace cl4;
+    CL4_REQUIRE(B >= 0 && C > 0 && M >= 0 && H > 0 && W > 0, CL4_EINVAL, "refine_with_point: bad shape B=%d C=%d M=%d H=%d W=%d", B,
+                C, M, H, W);
+    CL4_REQUIRE(gt_seg && label && offsets && out_offset && out_weight && (M == 0 || (points && keep)), CL4_EINVAL,
+                "refine_with_point: null pointer");
+    CL4_REQUIRE((long long)H * W < (1ll << 31) - 256 && B <= 65535, CL4_EUNSUPPORTED, "refine_with_point: shape too large");
+    if (B == 0) return CL4_OK;
+    dim3 grid(ceil_div(H * W, 256), B);
+    refine_with_point_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gt_seg, label, points, keep, offsets, out_offset, out_weight, C,
+                                                                      M, H, W);
+    return check_launch("refine_with_point");
+}
 
 extern "C" int cl4_group_pixels(const long long* ctr, const int* count_dev, int Kc, int ctr_stride,
                                 const float* offsets, const unsigned char* fg, long long* ids, int N, int H, int W,

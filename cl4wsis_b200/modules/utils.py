@@ -306,6 +306,42 @@ def refine_label_generation(seg_map, center_map, offset_map, label, gt_seg_map, 
     return out
 
 
+def refine_label_generation_with_point(seg_map, gt_point_cls, offset_map, label, gt_seg_map, args=None):
+    """Refined-label generation with point labels — modules/utils.py:388-460, same signature and result dict
+    ({'offset': [B,2,H,W], 'weight': [B,1,H,W]} float32 on the inputs' device).
+
+    gt_point_cls [B,C,MAX_NUM_POINTS,2] (y, x), rows with y == 0 or x == 0 are padding (the reference's filter, :436);
+    ``seg_map`` is only shape-checked (the reference computes a softmax of it that it never uses, :412-413) and ``args`` is
+    unused there as well.  One launch for the whole batch, no host synchronisation (the reference: a `group_pixels` pass per
+    (image, class) and a `torch.where` per instance)."""
+    lib = _lib.load()
+    _lib.require_cuda(offset_map, "offset_map")
+    dev = offset_map.device
+    off = offset_map.detach()
+    if off.dtype != torch.float32:
+        raise TypeError("refine_label_generation_with_point: offset_map must be float32")
+    off = off.contiguous()
+    B, two, H, W = off.shape
+    if two != 2 or seg_map.shape[0] != B or tuple(seg_map.shape[-2:]) != (H, W):
+        raise ValueError("refine_label_generation_with_point: seg_map [B,C+1,H,W] and offset_map [B,2,H,W] do not match")
+    lab = label.detach().to(device=dev, dtype=torch.float32).contiguous()
+    C = lab.shape[1]
+    gt = gt_seg_map.detach().to(device=dev, dtype=torch.int64).contiguous()
+    p = gt_point_cls.detach().to(dev)
+    if p.dim() != 4 or p.shape[0] != B or p.shape[1] != C or p.shape[3] != 2:
+        raise ValueError("refine_label_generation_with_point: gt_point_cls must be [B,C,MAX_NUM_POINTS,2]")
+    M = p.shape[2]
+    keep = ((p[..., 0] != 0) & (p[..., 1] != 0)).to(torch.uint8).contiguous()   # the filter of :436 on the caller's values
+    pts = p.to(torch.int32).to(torch.int64).contiguous()                          # np.int32(...) then .long() (:437, :442)
+    with torch.cuda.device(dev):
+        out_o = torch.empty((B, 2, H, W), dtype=torch.float32, device=dev)
+        out_w = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+        _lib.check(lib.cl4_refine_labels_with_point(_lib.ptr(gt), _lib.ptr(lab), _lib.ptr(pts), _lib.ptr(keep), _lib.ptr(off),
+                                                    _lib.ptr(out_o), _lib.ptr(out_w), B, C, M, H, W, _lib.stream_ptr(dev)),
+                   "refine_label_generation_with_point")
+    return {'offset': out_o, 'weight': out_w}
+
+
 def pseudo_label_generation_batch(seg_gt, peaks, cls_label, pseudo_thresh, sigma):
     """The per-image loop of train.py:451-477 — points from ``peak_extract`` filtered by
     ``pseudo_thresh``, then ``pseudo_label_generation`` (modules/utils.py:179-253) per image — for the

@@ -218,6 +218,16 @@ int cl4_refine_labels(const float* seg_logits, const float* center, const float*
                       float* out_center, float* out_offset, float* out_weight, int* status_out, int B, int C,
                       int H, int W, void* scratch, size_t scratch_bytes, cl4_stream_t stream);
 
+/* refine_label_generation_with_point — modules/utils.py:388-460 (point supervision; not reached by train.py), for a batch
+ * in one launch.  gt_seg [B,H,W] int64 labels; label [B,C]; points [B,C,M,2] int64 (y,x) with keep [B,C,M] bytes: non-zero =
+ * the point survives the reference's filter `gt_y != 0 and gt_x != 0` (:436, applied to the caller's values before the
+ * int32 conversion of :437); offsets [B,2,H,W].  Every pixel whose gt class is valid (:431) and has a kept point gets
+ * out_weight [B,1,H,W] = 1 and out_offset [B,2,H,W] = nearest kept point - pixel, nearest by group_pixels' arithmetic with
+ * the first minimum winning (:444); all other pixels 0. */
+int cl4_refine_labels_with_point(const long long* gt_seg, const float* label, const long long* points,
+                                 const unsigned char* keep, const float* offsets, float* out_offset, float* out_weight,
+                                 int B, int C, int M, int H, int W, cl4_stream_t stream);
+
 /* ------------------------------------------------------------------------- *
  * get_ins_map — dataset/utils.py:795-902, the validation post-processing (Trainer.validate,
  * train.py:622), for one image with no host round trip per class / contour / instance.

@@ -532,6 +532,39 @@ def test_refine_label_generation_per_contour_golden(cl4, golden_more, ci):
     _check_refine(mu.refine_label_generation_per_contour(*ins, topk, args), g, k)
 
 
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_refine_label_generation_with_point_golden(cl4, golden_more, ci):
+    """modules/utils.py:388-460 against the reference fixtures: bit-exact offsets and weights."""
+    from cl4wsis_b200.modules import utils as mu
+    g = golden_more("point")
+    k = f"point_{ci}__"
+    r = mu.refine_label_generation_with_point(cuda(g[k + "seg"]), cuda(g[k + "points"]), cuda(g[k + "off"]), cuda(g[k + "label"]),
+                                              cuda(g[k + "gt"]), None)
+    assert np.array_equal(r["offset"].cpu().numpy(), g[k + "offset"])
+    assert np.array_equal(r["weight"].cpu().numpy(), g[k + "weight"])
+
+
+def test_refine_label_generation_with_point_random_vs_oracle(cl4, oracle):
+    from cl4wsis_b200.modules import utils as mu
+    rng = np.random.default_rng(11)
+    B, C, M, H, W = 3, 20, 12, 200, 333
+    gt = rng.integers(0, C + 2, (B, H // 8 + 1, W // 8 + 1)).repeat(8, 1).repeat(8, 2)[:, :H, :W].astype(np.int64)  # incl. label C + 1
+    lab = (rng.random((B, C)) < 0.7).astype(np.float32)
+    pts = np.zeros((B, C, M, 2), np.int64)
+    for b in range(B):
+        for c in range(C):
+            n = rng.integers(0, M + 1)
+            pts[b, c, :n, 0] = rng.integers(0, H, n)     # a zero coordinate now and then: filtered
+            pts[b, c, :n, 1] = rng.integers(0, W, n)
+    off = (rng.standard_normal((B, 2, H, W)) * 20).astype(np.float32)
+    seg = np.zeros((B, C + 1, H, W), np.float32)
+    r = mu.refine_label_generation_with_point(cuda(seg), cuda(pts), cuda(off), cuda(lab), cuda(gt), None)
+    o = oracle.labelgen.refine_label_generation_with_point(seg, pts, off, lab, gt)
+    assert np.array_equal(r["offset"].cpu().numpy(), o["offset"])
+    assert np.array_equal(r["weight"].cpu().numpy(), o["weight"])
+    assert 0 < (o["weight"] > 0).mean() < 1
+
+
 def test_refine_label_generation_overflow_falls_back(cl4, golden_more):
     """A degenerate top_k (>= centres of a contour) trips the status word; the drop-in then answers
     through the per-contour path, which reproduces the reference's degenerate branch."""

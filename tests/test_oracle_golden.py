@@ -148,6 +148,18 @@ def test_refine_label_generation_matches_reference(golden_more, oracle):
     assert (g["refine_0__weight"] > 0).sum() > 1000 and (g["refine_3__weight"] > 0).sum() == 0
 
 
+def test_refine_label_generation_with_point_matches_reference(golden_more, oracle):
+    """modules/utils.py:388-460 (point supervision): offsets and weights bit-exact, including the reference's y != 0 and
+    x != 0 point filter, invalid classes, duplicate points and the empty case."""
+    g = golden_more("point")
+    for ci in range(int(g["n"])):
+        k = f"point_{ci}__"
+        r = oracle.labelgen.refine_label_generation_with_point(g[k + "seg"], g[k + "points"], g[k + "off"], g[k + "label"], g[k + "gt"])
+        assert np.array_equal(r["offset"], g[k + "offset"]), ci
+        assert np.array_equal(r["weight"], g[k + "weight"]), ci
+    assert (g["point_0__weight"] > 0).sum() > 1000 and (g["point_2__weight"] > 0).sum() == 0
+
+
 def test_smoothing_and_pseudo_label_generation_match_reference(golden_more, oracle):
     g = golden_more("pseudo")
     for i in range(int(g["smooth__n"])):
