@@ -385,7 +385,11 @@ __device__ __forceinline__ void duo_patcher(const DuoCtx& cx) {
 template <int G, bool kFar>
 __device__ __forceinline__ void duo_group(const DuoCtx& cx, const DuoOut& out) {
     static_assert((kDParts & (kDParts - 1)) == 0, "partial-sum buffers: a power of two");
-    const int tid = threadIdx.x, lane = tid & 31;
+    int tid = threadIdx.x;
+    // kept in a register (opaque to the compiler): rematerialised, it costs an S2R plus its ~25 cycles of latency in front of
+    // the weight-batch address of every item, on group B's critical path (-1.2 % per sweep)
+    asm volatile("" : "+r"(tid));
+    const int lane = tid & 31;
     const int tg = tid - G * kLGroupThreads;
     constexpr bool kT = (G == 1) && kFar && kDTmem;  // near weights in tensor memory
 
