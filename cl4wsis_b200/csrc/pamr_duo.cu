@@ -389,6 +389,7 @@ __device__ __forceinline__ void duo_group(const DuoCtx& cx, const DuoOut& out) {
     // kept in a register (opaque to the compiler): rematerialised, it costs an S2R plus its ~25 cycles of latency in front of
     // the weight-batch address of every item, on group B's critical path (-1.2 % per sweep)
     asm volatile("" : "+r"(tid));
+    tid = __shfl_sync(0xffffffffu, tid, tid & 31);  // opaque to ptxas as well (it rematerialises special-register reads): -0.3 %
     const int lane = tid & 31;
     const int tg = tid - G * kLGroupThreads;
     constexpr bool kT = (G == 1) && kFar && kDTmem;  // near weights in tensor memory
@@ -463,6 +464,11 @@ __device__ __forceinline__ void duo_group(const DuoCtx& cx, const DuoOut& out) {
             u64* const pp = pp0 + (it & (kDParts - 1)) * kDPartCells;
             const uint32_t pb8 = 32u * (it & (kDParts - 1)), part_phase = (it / kDParts) & 1u;
             mbar_wait_u32(ready0 + 8u * stage, full_phase);
+            // Group A probes the partial-sum buffer it will fill at the end of the item now (test_wait, non-blocking): the buffer
+            // is nearly always free, and a blocking try_wait costs ~90 cycles of latency even then (-0.4 % per sweep; the same
+            // probe for the next item's window gained nothing).
+            bool part_free = false;
+            if (G == 0) part_free = it < (uint32_t)kDParts || mbar_test_u32(pempty0 + pb8, part_phase ^ 1u);
 
 #pragma unroll
             for (int i = 0; i < kLPx; ++i) acc[i] = 0ull;
@@ -488,7 +494,7 @@ __device__ __forceinline__ void duo_group(const DuoCtx& cx, const DuoOut& out) {
             }
             // A's warp j and B's warp j own the same 8 rows of the tile, so the hand-over is per warp pair
             if (G == 0) {
-                if (it >= (uint32_t)kDParts) mbar_wait_u32(pempty0 + pb8, part_phase ^ 1u);
+                if (!part_free) mbar_wait_u32(pempty0 + pb8, part_phase ^ 1u);
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
 #pragma unroll

@@ -27,14 +27,17 @@ constexpr int kFusedMaxDim = 64;
 //   int_masks_soft[:, 1:] *= l1h[:, :, None, None]      -> gated values go to `mask_out`
 //   pseudo_gtmask (wss/single_stage.py:18-40): plane maximum (NaN-propagating), x cutoff_bkg / cutoff_top, floored at
 //   cutoff_low -> thr[b, c]; pseudo = (mask > thr), pixels claimed by more than one class cleared.
-// The ambiguity rule couples all classes of a pixel, and the classes of an image are spread over several CTAs: every CTA
-// publishes its gated planes and thresholds, then takes a ticket from done[b]; the CTA that draws the last ticket of its image
-// writes the pseudo labels of the whole image (C x H x W <= 81 x 64 x 64 values, from L2).
+// The ambiguity rule couples all classes of a pixel, and the classes of an image are spread over several CTAs (not
+// necessarily co-resident): every CTA writes the tentative pseudo labels of its own planes (mask > thr) and counts its claims
+// per pixel in cnt[b] (atomicAdd), then takes a ticket from done[b]; the CTA that draws the last ticket of its image clears the
+// pixels claimed more than once -- O(H x W) reads plus C stores per ambiguous pixel instead of a pass over all C x H x W
+// values by one CTA (which cost 260 us at C = 81, 56 x 56).
 struct Phase1Epilogue {
     const float* labels;  // [B, C-1] or nullptr
     float* pseudo;        // [B, C, H, W]
     float* thr;           // [B, C]
     int* done;            // [B], zeroed by the prologue kernel
+    int* cnt;             // [B, H, W] classes claiming each pixel, zeroed by the prologue kernel
     float cutoff_top, cutoff_bkg, cutoff_low;
 };
 
@@ -137,6 +140,13 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
 #pragma unroll
                     for (int i = 0; i < kPx; ++i)
                         if ((valid >> i) & 1u) o[(size_t)(i * kRowGap) * W] = acc[i];
+                    if (kP1) {  // the epilogue compares the gated values with the plane's threshold: keep them on-chip (the other
+                                // ping-pong plane is free in the last iteration)
+                        float* o2 = plane(c, nxt) + sbase;
+#pragma unroll
+                        for (int i = 0; i < kPx; ++i)
+                            if ((valid >> i) & 1u) o2[i * kRowGap * PITCH] = acc[i];
+                    }
                 } else {
                     float* o = plane(c, nxt) + sbase;
 #pragma unroll
@@ -172,30 +182,41 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
     }
 
     if (kP1) {
-        __syncthreads();  // s_cmax complete; this CTA's gated planes are on their way to L2
+        __shared__ float s_thr[kCpbCap];
+        __syncthreads();  // s_cmax complete; this CTA's gated planes are visible to the whole CTA
         if (tid < nc) {
             float mx = s_cmax[tid * (kSweepThreads / 32)];
             for (int wi = 1; wi < kSweepThreads / 32; ++wi) mx = nanmax(mx, s_cmax[tid * (kSweepThreads / 32) + wi]);
             const int cls = c0 + tid;
             const float scaled = __fmul_rn(mx, cls == 0 ? ep.cutoff_bkg : ep.cutoff_top);  // mask_max[:, :1] *= bkg; [:, 1:] *= top
-            ep.thr[(size_t)b * C + cls] = (ep.cutoff_low > scaled || ep.cutoff_low != ep.cutoff_low) ? ep.cutoff_low : scaled;
+            const float th = (ep.cutoff_low > scaled || ep.cutoff_low != ep.cutoff_low) ? ep.cutoff_low : scaled;
+            s_thr[tid] = th;
+            ep.thr[(size_t)b * C + cls] = th;
         }
-        __threadfence();  // every thread: its stores to mask_out / thr are visible device-wide before the ticket is drawn
+        __syncthreads();
+        int* cnt = ep.cnt + (size_t)b * HW;
+        const int fin = (num_iter & 1);  // the plane the last iteration wrote: nxt of it = num_iter - 1
+        for (int c = 0; c < nc; ++c) {
+            const float* gm = plane(c, fin) + kHalo * PITCH + kHalo;
+            float* po = ep.pseudo + ((size_t)b * C + c0 + c) * HW;
+            const float th = s_thr[c];
+            for (int y = wrp; y < H; y += kSweepThreads / 32)
+                for (int x = lane; x < W; x += 32) {
+                    const bool on = gm[y * PITCH + x] > th;
+                    po[(size_t)y * W + x] = on ? 1.f : 0.f;
+                    if (on) atomicAdd(cnt + y * W + x, 1);
+                }
+        }
+        __threadfence();  // every thread: its pseudo labels and claims are visible device-wide before the ticket is drawn
         __syncthreads();
         if (tid == 0) s_last = (atomicAdd(ep.done + b, 1) == (int)gridDim.x - 1);
         __syncthreads();
         if (s_last) {
             __threadfence();
-            const float* gm = mask_out + (size_t)b * C * HW;
-            const float* th = ep.thr + (size_t)b * C;
             float* po = ep.pseudo + (size_t)b * C * HW;
-            for (int i = tid; i < (int)HW; i += kSweepThreads) {
-                int n = 0;
-                for (int c = 0; c < C; ++c) n += (__ldcg(gm + (size_t)c * HW + i) > __ldcg(th + c));
-                const bool clear = n > 1;  // ambiguous=True (train.py:384)
-                for (int c = 0; c < C; ++c)
-                    po[(size_t)c * HW + i] = (!clear && __ldcg(gm + (size_t)c * HW + i) > __ldcg(th + c)) ? 1.f : 0.f;
-            }
+            for (int i = tid; i < (int)HW; i += kSweepThreads)
+                if (__ldcg(cnt + i) > 1)  // ambiguous=True (train.py:384): a pixel claimed by several classes belongs to none
+                    for (int c = 0; c < C; ++c) po[(size_t)c * HW + i] = 0.f;
         }
     }
 }
@@ -292,9 +313,9 @@ int launch_pamr_fused(const float* w, const float* mask_in, float* mask_out, int
 
 // The same launch with the phase-1 epilogue: mask_out receives the label-gated masks, pseudo / thr as Phase1Epilogue says.
 int launch_pamr_fused_phase1(const float* w, const float* mask_in, float* gated_out, float* pseudo_out, float* thr, int* done,
-                             const float* labels, float cutoff_top, float cutoff_bkg, float cutoff_low, int B, int C, int H, int W,
+                             int* cnt, const float* labels, float cutoff_top, float cutoff_bkg, float cutoff_low, int B, int C, int H, int W,
                              int num_iter, const Dilations& dil, int D, cudaStream_t s) {
-    Phase1Epilogue ep{labels, pseudo_out, thr, done, cutoff_top, cutoff_bkg, cutoff_low};
+    Phase1Epilogue ep{labels, pseudo_out, thr, done, cnt, cutoff_top, cutoff_bkg, cutoff_low};
     t_ep = &ep;
     const int rc = launch_pamr_fused(w, mask_in, gated_out, B, C, H, W, num_iter, dil, D, s);
     t_ep = nullptr;

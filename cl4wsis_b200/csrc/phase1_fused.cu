@@ -1,7 +1,7 @@
 // The phase-1 pseudo-label step around PAMR (reference train.py:372-385) in TWO launches for feature-resolution maps
 // (at most 64 x 64, D <= 6, dilations <= 24 -- the regime the trainer runs):
 //
-//   1. phase1_prologue_kernel, one CTA per (image, 32 x 32 tile):
+//   1. phase1_prologue_kernel, four CTAs per (image, 32 x 32 tile), each owning eight rows of the tile:
 //        im = F.interpolate(denorm(images), int_masks.shape[-2:], "bilinear", align_corners=True)   train.py:376-378
 //          -> evaluated straight into a replicate-padded shared-memory window (tile + 24-pixel halo), never written out;
 //        affinity weights of the tile's pixels from that window (wss/modules.py:141-146)  -> tile-major scratch;
@@ -22,76 +22,109 @@ struct DenormCoef {
 };
 
 int launch_pamr_fused_phase1(const float* w, const float* mask_in, float* gated_out, float* pseudo_out, float* thr, int* done,
-                             const float* labels, float cutoff_top, float cutoff_bkg, float cutoff_low, int B, int C, int H, int W,
+                             int* cnt, const float* labels, float cutoff_top, float cutoff_bkg, float cutoff_low, int B, int C, int H, int W,
                              int num_iter, const Dilations& dil, int D, cudaStream_t s);
+
+constexpr int kP1Slabs = 4;                       // slabs per (image, tile): slab z owns the tile rows 8z .. 8z+7 (one row per warp);
+                                                  // CTAs z < 4 do window + weights of slab z, CTAs z >= 4 the softmax of slab z - 4
+constexpr int kP1SlabRows = kTile / kP1Slabs;     // 8
+constexpr int kP1WinRows = kP1SlabRows + 2 * kHalo;  // 56 window rows feed a slab
 
 template <int D, class DS>
 __global__ void __launch_bounds__(256)
 phase1_prologue_kernel(const float* __restrict__ images, const float* __restrict__ logits, float* __restrict__ soft,
-                       float* __restrict__ wts, int* __restrict__ done, int C, int Hi, int Wi, int h, int w, float sy, float sx,
-                       DenormCoef a, Dilations dil) {
+                       float* __restrict__ wts, int* __restrict__ done, int* __restrict__ cnt, int C, int Hi, int Wi, int h, int w,
+                       float sy, float sx, DenormCoef a, Dilations dil) {
     constexpr int P = 8 * D;
-    extern __shared__ __align__(16) float win[];  // [3][kBox][kBox]
+    extern __shared__ __align__(16) float win[];  // [3][kBox][kBox]; this CTA fills rows wy0 .. wy0+55
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int tiles_x = ceil_div(w, kTile);
     const int tyi = blockIdx.x / tiles_x;
     const int y0 = tyi * kTile, x0 = (blockIdx.x - tyi * tiles_x) * kTile;
     const int b = blockIdx.y;
-    if (blockIdx.x == 0 && tid == 0) done[b] = 0;  // ticket counter of the epilogue (pamr_fused.cu)
-
-    // ---- the shrunk, denormalised image: window cell (wy, wx) = pixel (clamp(y0 + wy - 24), clamp(x0 + wx - 24)).
-    // Arithmetic of cl4_denorm_resize_ac (phase1.cu): denorm on each of the four taps with separate roundings for the
-    // multiply and the add (Tensor.mul_().add_()), then ATen's align_corners=True bilinear combination.
-    for (int i = tid; i < 3 * kBox * kBox; i += 256) {
-        const int k = i / (kBox * kBox), r = i - k * (kBox * kBox);
-        const int wy = r / kBox, wx = r - wy * kBox;
-        const int y = clampi(y0 + wy - kHalo, 0, h - 1), x = clampi(x0 + wx - kHalo, 0, w - 1);
-        const float* src = images + ((size_t)b * 3 + k) * Hi * Wi;
-        const float fy = __fmul_rn(sy, (float)y), fx = __fmul_rn(sx, (float)x);
-        const int ya = min((int)fy, Hi - 1), xa = min((int)fx, Wi - 1);
-        const int yb = ya + (ya < Hi - 1), xb = xa + (xa < Wi - 1);
-        const float ly1 = fy - (float)ya, ly0 = 1.f - ly1;
-        const float lx1 = fx - (float)xa, lx0 = 1.f - lx1;
-        auto tap = [&](int yy, int xx) {
-            const float v = __ldg(src + (size_t)yy * Wi + xx);
-            return a.apply ? __fadd_rn(__fmul_rn(v, a.mul[k]), a.add[k]) : v;
-        };
-        const float top = __fadd_rn(__fmul_rn(lx0, tap(ya, xa)), __fmul_rn(lx1, tap(ya, xb)));
-        const float bot = __fadd_rn(__fmul_rn(lx0, tap(yb, xa)), __fmul_rn(lx1, tap(yb, xb)));
-        win[i] = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
-    }
-
-    // ---- softmax over the classes for the tile's pixels (independent of the window: overlaps its loads)
+    const int wy0 = (blockIdx.z % kP1Slabs) * kP1SlabRows;
+    if (blockIdx.x == 0 && blockIdx.z == 0 && tid == 0) done[b] = 0;  // ticket counter of the epilogue (pamr_fused.cu)
     const size_t hw = (size_t)h * w;
-    for (int i = tid; i < kTile * kTile; i += 256) {
-        const int y = y0 + (i >> 5), x = x0 + (i & 31);
+
+    if (blockIdx.z >= kP1Slabs) {
+        // ---- softmax over the classes for the slab's pixels, one per thread, in CTAs of their own: it is as long as the rest
+        // of the prologue at C = 81 and independent of it
+        const int y = y0 + wy0 + wrp, x = x0 + lane;
         if (y < h && x < w) {
+            cnt[(size_t)b * hw + (size_t)y * w + x] = 0;  // claims per pixel, counted by the epilogue (pamr_fused.cu)
             const float* p = logits + (size_t)b * C * hw + (size_t)y * w + x;
             float* o = soft + (size_t)b * C * hw + (size_t)y * w + x;
             float mx = p[0];
+#pragma unroll 8
             for (int c = 1; c < C; ++c) mx = fmaxf(mx, p[(size_t)c * hw]);
             float z = 0.f;
+#pragma unroll 8
             for (int c = 0; c < C; ++c) z += expf(p[(size_t)c * hw] - mx);
+#pragma unroll 8
             for (int c = 0; c < C; ++c) o[(size_t)c * hw] = expf(p[(size_t)c * hw] - mx) / z;
+        }
+        return;
+    }
+
+    // ---- the shrunk, denormalised image: window cell (wy, wx) = pixel (clamp(y0 + wy - 24), clamp(x0 + wx - 24)).
+    // Only the DISTINCT pixels are evaluated -- the cells that lie inside the map (for a 32 x 32 map 1024 of the window's 6400
+    // cells per channel) -- a warp per (channel, row), lanes along x, several rows in flight; the clamped cells are copies.
+    // Arithmetic of cl4_denorm_resize_ac (phase1.cu): denorm on each of the four taps with separate roundings for the
+    // multiply and the add (Tensor.mul_().add_()), then ATen's align_corners=True bilinear combination.
+    const int ya = max(0, y0 + wy0 - kHalo), yb = min(h, y0 + wy0 + kP1WinRows - kHalo);  // map rows inside this slab's window
+    const int xa = max(0, x0 - kHalo), xb = min(w, x0 + kBox - kHalo);
+    const int ny = max(yb - ya, 0);
+    // (Batching the taps of four rows before their first use was measured slower: the step is bound by L2 sectors -- a lane's
+    // two x taps share one 32-byte sector of which 8 bytes are used -- not by latency.  Every CTA of a small map needs nearly
+    // the whole shrunk image, so this work is repeated by the 4 slabs x tiles of an image: 58 of the prologue's 60 us at 56 x 56.)
+#pragma unroll 4
+    for (int r = wrp; r < 3 * ny; r += 8) {
+        const int k = r / ny, y = ya + (r - k * ny);
+        const float* src = images + ((size_t)b * 3 + k) * Hi * Wi;
+        const float fy = __fmul_rn(sy, (float)y);
+        const int y_lo = min((int)fy, Hi - 1), y_hi = y_lo + (y_lo < Hi - 1);
+        const float ly1 = fy - (float)y_lo, ly0 = 1.f - ly1;
+        float* dst = win + ((size_t)k * kBox + (y - y0 + kHalo)) * kBox + kHalo - x0;
+        for (int x = xa + lane; x < xb; x += 32) {
+            const float fx = __fmul_rn(sx, (float)x);
+            const int x_lo = min((int)fx, Wi - 1), x_hi = x_lo + (x_lo < Wi - 1);
+            const float lx1 = fx - (float)x_lo, lx0 = 1.f - lx1;
+            auto tap = [&](int yy, int xx) {
+                const float v = __ldg(src + (size_t)yy * Wi + xx);
+                return a.apply ? __fadd_rn(__fmul_rn(v, a.mul[k]), a.add[k]) : v;
+            };
+            const float top = __fadd_rn(__fmul_rn(lx0, tap(y_lo, x_lo)), __fmul_rn(lx1, tap(y_lo, x_hi)));
+            const float bot = __fadd_rn(__fmul_rn(lx0, tap(y_hi, x_lo)), __fmul_rn(lx1, tap(y_hi, x_hi)));
+            dst[x] = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+        }
+    }
+
+    __syncthreads();
+    // ---- replicate padding: every cell of the slab's 56 window rows that lies outside the map copies the clamped in-map cell
+    for (int r = wrp; r < 3 * kP1WinRows; r += 8) {
+        const int k = r / kP1WinRows, wy = wy0 + (r - k * kP1WinRows);
+        const int sy_ = clampi(y0 + wy - kHalo, 0, h - 1) - y0 + kHalo;
+        float* row = win + ((size_t)k * kBox + wy) * kBox;
+        const float* srow = win + ((size_t)k * kBox + sy_) * kBox;
+        for (int wx = lane; wx < kBox; wx += 32) {
+            const int sx_ = clampi(x0 + wx - kHalo, 0, w - 1) - x0 + kHalo;
+            if (sy_ != wy || sx_ != wx) row[wx] = srow[sx_];
         }
     }
     __syncthreads();
 
-    // ---- affinity weights, tile-major [tile][P/4][32][32] float4 (what pamr_fused_kernel reads)
+    // ---- affinity weights of the slab's row of this warp, tile-major [tile][P/4][32][32] float4 (what pamr_fused_kernel reads)
     float4* o = reinterpret_cast<float4*>(wts) + ((size_t)b * gridDim.x + blockIdx.x) * (P / 4 * kTile * kTile) + lane;
-#pragma unroll 1
-    for (int i = 0; i < 4; ++i) {
-        const int row = wrp + 8 * i;
-        float logit[P];
-        pixel_affinity<D, DS>(win + (row + kHalo) * kBox + lane + kHalo, 3, kBox * kBox, kBox, dil, logit);
+    const int row = wy0 + wrp;
+    float logit[P];
+    pixel_affinity<D, DS>(win + (row + kHalo) * kBox + lane + kHalo, 3, kBox * kBox, kBox, dil, logit);
 #pragma unroll
-        for (int g = 0; g < P / 4; ++g)
-            o[(size_t)g * (kTile * kTile) + row * kTile] = make_float4(logit[4 * g], logit[4 * g + 1], logit[4 * g + 2], logit[4 * g + 3]);
-    }
+    for (int g = 0; g < P / 4; ++g)
+        o[(size_t)g * (kTile * kTile) + row * kTile] = make_float4(logit[4 * g], logit[4 * g + 1], logit[4 * g + 2], logit[4 * g + 3]);
 }
 
 template <int D, class DS>
-static int launch_prologue_one(const float* images, const float* logits, float* soft, float* wts, int* done, int B, int C, int Hi,
+static int launch_prologue_one(const float* images, const float* logits, float* soft, float* wts, int* done, int* cnt, int B, int C, int Hi,
                                int Wi, int h, int w, const DenormCoef& a, const Dilations& dil, cudaStream_t s) {
     auto kern = phase1_prologue_kernel<D, DS>;
     const size_t smem = sizeof(float) * 3 * kBox * kBox;
@@ -102,26 +135,26 @@ static int launch_prologue_one(const float* images, const float* logits, float* 
     }
     const float sy = (h > 1) ? (float)(Hi - 1) / (float)(h - 1) : 0.f;
     const float sx = (w > 1) ? (float)(Wi - 1) / (float)(w - 1) : 0.f;
-    dim3 grid(ceil_div(w, kTile) * ceil_div(h, kTile), B);
-    kern<<<grid, 256, smem, s>>>(images, logits, soft, wts, done, C, Hi, Wi, h, w, sy, sx, a, dil);
+    dim3 grid(ceil_div(w, kTile) * ceil_div(h, kTile), B, 2 * kP1Slabs);
+    kern<<<grid, 256, smem, s>>>(images, logits, soft, wts, done, cnt, C, Hi, Wi, h, w, sy, sx, a, dil);
     return check_launch("phase1_prologue");
 }
 
 template <int D>
-static int launch_prologue_D(const float* images, const float* logits, float* soft, float* wts, int* done, int B, int C, int Hi,
+static int launch_prologue_D(const float* images, const float* logits, float* soft, float* wts, int* done, int* cnt, int B, int C, int Hi,
                              int Wi, int h, int w, const DenormCoef& a, const Dilations& dil, cudaStream_t s) {
     bool voc6 = (D == 6), voc5 = (D == 5);
     for (int i = 0; i < D && i < 6; ++i) {
         voc6 = voc6 && dil.d[i] == DilVoc6::get(i);
         voc5 = voc5 && dil.d[i] == DilVoc5::get(i);
     }
-    if (D == 6 && voc6) return launch_prologue_one<6, DilVoc6>(images, logits, soft, wts, done, B, C, Hi, Wi, h, w, a, dil, s);
-    if (D == 5 && voc5) return launch_prologue_one<5, DilVoc5>(images, logits, soft, wts, done, B, C, Hi, Wi, h, w, a, dil, s);
-    return launch_prologue_one<D, DilRuntime>(images, logits, soft, wts, done, B, C, Hi, Wi, h, w, a, dil, s);
+    if (D == 6 && voc6) return launch_prologue_one<6, DilVoc6>(images, logits, soft, wts, done, cnt, B, C, Hi, Wi, h, w, a, dil, s);
+    if (D == 5 && voc5) return launch_prologue_one<5, DilVoc5>(images, logits, soft, wts, done, cnt, B, C, Hi, Wi, h, w, a, dil, s);
+    return launch_prologue_one<D, DilRuntime>(images, logits, soft, wts, done, cnt, B, C, Hi, Wi, h, w, a, dil, s);
 }
 
 struct Phase1Layout {
-    size_t wts, soft, thr, done, bytes;
+    size_t wts, soft, thr, done, cnt, bytes;
 };
 static Phase1Layout phase1_layout(int B, int C, int h, int w, int D) {
     Phase1Layout L;
@@ -136,6 +169,7 @@ static Phase1Layout phase1_layout(int B, int C, int h, int w, int D) {
     L.soft = take(sizeof(float) * (size_t)B * C * h * w);
     L.thr = take(sizeof(float) * (size_t)B * C);
     L.done = take(sizeof(int) * (size_t)B);
+    L.cnt = take(sizeof(int) * (size_t)B * h * w);
     L.bytes = off;
     return L;
 }
@@ -174,6 +208,7 @@ extern "C" int cl4_phase1_pseudo_labels(const float* images, const float* int_ma
     float* soft = reinterpret_cast<float*>(base + L.soft);
     float* thr = reinterpret_cast<float*>(base + L.thr);
     int* done = reinterpret_cast<int*>(base + L.done);
+    int* cnt = reinterpret_cast<int*>(base + L.cnt);
     DenormCoef a{{1.f, 1.f, 1.f}, {0.f, 0.f, 0.f}, mean ? 1 : 0};
     if (mean)
         for (int k = 0; k < 3; ++k) {
@@ -183,14 +218,14 @@ extern "C" int cl4_phase1_pseudo_labels(const float* images, const float* int_ma
     cudaStream_t s = (cudaStream_t)stream;
     int rc = CL4_EUNSUPPORTED;
     switch (D) {
-        case 1: rc = launch_prologue_D<1>(images, int_masks, soft, wts, done, B, C, Hi, Wi, h, w, a, dil, s); break;
-        case 2: rc = launch_prologue_D<2>(images, int_masks, soft, wts, done, B, C, Hi, Wi, h, w, a, dil, s); break;
-        case 3: rc = launch_prologue_D<3>(images, int_masks, soft, wts, done, B, C, Hi, Wi, h, w, a, dil, s); break;
-        case 4: rc = launch_prologue_D<4>(images, int_masks, soft, wts, done, B, C, Hi, Wi, h, w, a, dil, s); break;
-        case 5: rc = launch_prologue_D<5>(images, int_masks, soft, wts, done, B, C, Hi, Wi, h, w, a, dil, s); break;
-        case 6: rc = launch_prologue_D<6>(images, int_masks, soft, wts, done, B, C, Hi, Wi, h, w, a, dil, s); break;
+        case 1: rc = launch_prologue_D<1>(images, int_masks, soft, wts, done, cnt, B, C, Hi, Wi, h, w, a, dil, s); break;
+        case 2: rc = launch_prologue_D<2>(images, int_masks, soft, wts, done, cnt, B, C, Hi, Wi, h, w, a, dil, s); break;
+        case 3: rc = launch_prologue_D<3>(images, int_masks, soft, wts, done, cnt, B, C, Hi, Wi, h, w, a, dil, s); break;
+        case 4: rc = launch_prologue_D<4>(images, int_masks, soft, wts, done, cnt, B, C, Hi, Wi, h, w, a, dil, s); break;
+        case 5: rc = launch_prologue_D<5>(images, int_masks, soft, wts, done, cnt, B, C, Hi, Wi, h, w, a, dil, s); break;
+        case 6: rc = launch_prologue_D<6>(images, int_masks, soft, wts, done, cnt, B, C, Hi, Wi, h, w, a, dil, s); break;
     }
     if (rc != CL4_OK) return rc;
-    return launch_pamr_fused_phase1(wts, soft, soft_out, pseudo_out, thr, done, l1h, cutoff_top, cutoff_bkg, cutoff_low, B, C, h, w,
+    return launch_pamr_fused_phase1(wts, soft, soft_out, pseudo_out, thr, done, cnt, l1h, cutoff_top, cutoff_bkg, cutoff_low, B, C, h, w,
                                     num_iter, dil, D, s);
 }

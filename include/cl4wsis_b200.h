@@ -268,9 +268,10 @@ int cl4_ins_masks(const int* inst_map, int n, int H, int W, unsigned char* masks
  *   when `ambiguous`.  thr_scratch: B*C floats.
  * ------------------------------------------------------------------------- */
 /* The whole of train.py:372-385 for feature-resolution maps (h, w <= 64; 1..6 dilations, each <= 24; num_iter >= 1) in TWO
- * launches: (1) per (image, 32x32 tile): denorm + align-corners shrink of the image into a shared-memory window, affinity
- * weights from it, class softmax; (2) all num_iter PAMR sweeps on-chip followed by label gating, plane maxima, thresholds
- * and pseudo_gtmask(ambiguous=True) -- the last CTA of an image to finish writes its pseudo labels.
+ * launches: (1) per (image, 32x32 tile, 8-row slab): denorm + align-corners shrink of the image into a shared-memory window,
+ * affinity weights from it; class softmax in CTAs of its own; (2) all num_iter PAMR sweeps on-chip followed by label gating,
+ * plane maxima, thresholds and pseudo_gtmask(ambiguous=True) -- every CTA writes the labels of its planes and counts its claims
+ * per pixel, the last CTA of an image to finish clears the pixels claimed more than once.
  * images [B,3,Hi,Wi], int_masks [B,C,h,w] logits, l1h [B,C-1] or NULL, mean / std: HOST arrays of three floats (NULL: no
  * denorm) -> soft_out [B,C,h,w] (int_masks_soft after gating), pseudo_out [B,C,h,w] (0/1).  CL4_EUNSUPPORTED outside the
  * stated range: use the separate entry points above. */
