@@ -19,6 +19,7 @@ iterations, nms kernel 41, threshold 0.3).  Prints ONE JSON line (rank 0).
                sampled every 20 ms (power / thermal steady state); `value` stays the K-step figure
   small_map    the trainer's real regime (train.py:376-379): phase1_pseudo_labels at 32x32 / 56x56
   extra_workloads  short runs of BASELINE configs 3 and 4 (N=1 only)
+  sbd_pass     BASELINE config 5: one 10 582-image pass sharded over the N ranks (device-resident, rolled synthetic batches)
   torch_gpu_baseline  the same step restated with stock PyTorch ops on this GPU (oracle/torch_ref.py)
 
 `--impl reference` times the oracle port alone (the reference itself is Python and does not
@@ -400,6 +401,38 @@ def run_workload(cl4, cfg, dev, first_image, steps, warmup, gen_device):
     return out
 
 
+def run_sbd_pass(cdist, step, inputs, rank, world, dev, n_images=10582):
+    """BASELINE configs[4]: one synthetic SBD-sized pass (10 582 images, C21, 512 x 512) of PAMR + centre NMS + grouping, images
+    sharded contiguously over the ranks (cl4wsis_b200.dist.shard_bounds), batches of B, no data-path collective.  Each rank
+    rolls its synthetic batch along the batch dimension from batch to batch; the tail batch runs full-size and only its real
+    images are counted.  The timed region includes the rolls and the per-batch checksum reductions."""
+    img, mask, heat, off = inputs
+    B = img.shape[0]
+    lo, hi = cdist.shard_bounds(n_images, rank, world)
+    n_mine = hi - lo
+    n_batches = (n_mine + B - 1) // B
+    ck_mask = torch.zeros((), dtype=torch.float64, device=dev)
+    ck_ids = torch.zeros((), dtype=torch.float64, device=dev)
+    cdist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(n_batches):
+        sft = k % B
+        xi, mi, hi_, oi = (torch.roll(t, sft, 0) for t in (img, mask, heat, off)) if sft else (img, mask, heat, off)
+        refined, ids, _, _ = step.run(xi, mi, hi_, oi)
+        real = min(B, n_mine - k * B)
+        ck_mask += refined[:real].sum(dtype=torch.float64)
+        ck_ids += ids[:real].sum(dtype=torch.float64)
+    e1.record()
+    torch.cuda.synchronize()
+    st = cdist.reduce_stats(n_mine, e0.elapsed_time(e1) / 1e3, float(ck_mask), float(ck_ids), device=dev)
+    return {"workload": "sbd_pass_10582_c21_512", "images": st["images"], "pass_seconds": st["elapsed_s"],
+            "value": st["images"] / st["elapsed_s"], "unit": UNIT, "n_gpus": world, "batches_per_rank": n_batches,
+            "checksums": {"mask": st["checksum_mask"], "ids": st["checksum_ids"]},
+            "note": "BASELINE configs[4]; timed region includes the batch rolls and the checksum reductions; max over ranks"}
+
+
 def time_small_maps(cl4, dev):
     """The regime the trainer really runs PAMR in (train.py:372-385): softmax -> denorm + shrink -> PAMR(10,
     [1,2,4,8,12]) -> label gating -> pseudo_gtmask on feature-resolution maps.  Per shape: microseconds per
@@ -582,6 +615,10 @@ def main():
         del pipe
         torch.cuda.empty_cache()
 
+    sbd = None
+    if args.workload == "voc_b16_c21_512" and not args.no_extras:  # every rank takes part
+        sbd = run_sbd_pass(cdist, step, (img, mask, heat, off), rank, world, dev)
+
     callers = small = extras = torch_gpu = None
     if rank == 0 and not args.no_callers:
         callers = time_callers(cfg, dev, 4321)
@@ -659,6 +696,8 @@ def main():
         line["small_map"] = small
     if extras is not None:
         line["extra_workloads"] = extras
+    if sbd is not None:
+        line["sbd_pass"] = sbd
     if torch_gpu is not None:
         line["torch_gpu_baseline"] = torch_gpu
     if world == 1 and not args.no_cpu_baseline:
