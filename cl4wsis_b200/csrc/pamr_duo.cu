@@ -276,6 +276,7 @@ struct DuoCtx {
     uint32_t tmem_base;      // 256 columns x 128 lanes of tensor memory (group B's near weights: current tile, next tile)
     const float* wts;
     int C, Cp, H, W, tiles_x, tiles_per_img, n_tiles, n_my, total, s0;
+    const int* meta;  // shared memory: {n_my, s0, number of visits}: what the visit loop of the compute warps reads instead of keeping it
 };
 
 // The producer (one thread of the third warpgroup): waits until all eight compute warps have released the stage it is about
@@ -416,8 +417,14 @@ __device__ __forceinline__ void duo_group(const DuoCtx& cx, const DuoOut& out) {
     // group B, weights in tensor memory: this warp's lane quadrant, columns [0,256) and [256,512) alternate between visits
     uint32_t tcur = cx.tmem_base + ((uint32_t)((tid >> 5) & 3) << 21), tnext = tcur + kDTileCols;
 
-    int tile = blockIdx.x, q = cx.s0, left = cx.total;
-    if (left > 0) {
+    // The visit sequence is a function of the visit number v alone: visit 0 = pairs s0 .. Cp-1 of the CTA's first tile, visits
+    // 1 .. n_my-1 = all pairs of its other tiles, and (s0 > 0) a last visit = pairs 0 .. s0-1 of the first tile again.  The loop
+    // keeps v and the item counter in registers and re-reads n_my / s0 from shared memory at every visit: with tile, pair and
+    // remaining-item counters live across the item loop ptxas spilled them, and a spilled word comes back from DRAM at a visit
+    // boundary (the weight stream evicts local memory from L1 and L2): ~1 000 cycles per reload, 4.5 % of group A's time.
+    const volatile int* const meta = cx.meta;
+    int tile = blockIdx.x;
+    if (meta[2] > 0) {
         if (kT) {
 #pragma unroll 1
             for (int b = 0; b < kDBatches; ++b) {
@@ -434,12 +441,17 @@ __device__ __forceinline__ void duo_group(const DuoCtx& cx, const DuoOut& out) {
     uint32_t it = 0;  // items done: partial-sum buffer it % kDParts, its phase (it / kDParts) & 1
     int stage = 0;
     uint32_t full_phase = 0;
-    while (left > 0) {
+#pragma unroll 1
+    for (int v = 0;; ++v) {
+        const int n_my = meta[0], s0 = meta[1];
+        if (v >= meta[2]) break;
         // ---- one visit: pairs q .. q + n_q - 1 of `tile`
-        const int n_q = min(cx.Cp - q, left);
-        int next_tile = tile + (int)gridDim.x;
-        if (next_tile >= cx.n_tiles) next_tile = blockIdx.x;
-        const bool switch_tile = (left > n_q) && (next_tile != tile);  // another tile follows: its weights are fetched during this visit
+        const int Cp = (cx.C + 1) >> 1;
+        const int q = (v == 0) ? s0 : 0;
+        const int n_q = (v == 0) ? Cp - s0 : ((v < n_my) ? Cp : s0);
+        const int nk = (v + 1 < n_my) ? v + 1 : 0;
+        const int next_tile = (int)blockIdx.x + nk * (int)gridDim.x;
+        const bool switch_tile = (v + 1 < meta[2]) && (next_tile != tile);  // another tile follows: its weights are fetched during this visit
         const float4* const nw = weight_ptr(next_tile);
         if (switch_tile && (lane & 7) == 0) {
             // the next visit's weights into L2 a whole visit ahead: four 128-byte lines per warp and float4 group
@@ -565,8 +577,6 @@ __device__ __forceinline__ void duo_group(const DuoCtx& cx, const DuoOut& out) {
             tcur = tnext;
             tnext = t;
         }
-        left -= n_q;
-        q = 0;
         tile = next_tile;
     }
 }
@@ -611,6 +621,13 @@ pamr_sweep_duo_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
     }
     constexpr bool kUseTmem = kFar && kDTmem;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cx.pempty + 4 * kDParts);
+    int* meta = reinterpret_cast<int*>(tmem_slot + 2);
+    cx.meta = meta;
+    if (threadIdx.x == 0) {
+        meta[0] = cx.n_my;
+        meta[1] = cx.s0;
+        meta[2] = cx.n_my == 0 ? 0 : cx.n_my + (cx.s0 > 0 ? 1 : 0);
+    }
     if (kUseTmem && (threadIdx.x >> 5) == kLGroupThreads / 32) {  // first warp of group B allocates (and frees) the columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kDTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
