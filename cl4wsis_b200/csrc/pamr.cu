@@ -330,6 +330,8 @@ extern "C" int cl4_pamr_forward_timed(const float* img, const float* mask_in, fl
     // CL4_SWEEP=v1 forces the register/L1 kernel, CL4_SWEEP=tma skips the fused small-map kernel
     // (A/B timing and tests of the other paths)
     // CL4_SWEEP=lattice / nolattice: take / skip the lattice sweep (pamr_lattice.cu; the default wherever it applies)
+    // (read per call on purpose: the parity tests and tools/abl.sh switch paths inside one process; a getenv is ~50 ns
+    // against >= 70 us for the shortest PAMR call)
     const char* force = getenv("CL4_SWEEP");
     const bool force_v1 = force && strcmp(force, "v1") == 0, force_tma = force && strcmp(force, "tma") == 0;
     const bool force_lat1 = force && strcmp(force, "lattice1") == 0;  // the one-class-per-window lattice sweep

@@ -39,18 +39,6 @@ namespace cl4 {
 
 typedef unsigned long long u64;
 
-
-#ifdef CL4_DUO_FAKEW  // ablation (wrong results): only CL4_DUO_FAKEW weight registers are live -- what would free registers buy?
-#define CL4_DUO_WIDX(k) ((k) % CL4_DUO_FAKEW)
-#else
-#define CL4_DUO_WIDX(k) (k)
-#endif
-#ifdef CL4_DUO_FAKEFAR  // ablation (wrong results): group B's 64 dilation-24 weights alias 16 live registers
-#define CL4_DUO_WIDX_FAR(k) ((k) % CL4_DUO_FAKEFAR)
-#else
-#define CL4_DUO_WIDX_FAR(k) CL4_DUO_WIDX(k)
-#endif
-
 constexpr int kDStages = CL4_DUO_STAGES;
 constexpr int kDParts = CL4_DUO_PARTS;
 constexpr int kDPitch = kLPitch;                   // window pitch in cells (84: A's half-warps hit 16 different bank pairs)
@@ -122,7 +110,7 @@ __device__ __forceinline__ void feed2(float (&w)[kLW], u64 (&acc)[kLPx], const u
                 const int di = r - i, dj = c - j;
                 if (is_tap(di, dj, s)) {
                     const int k = (i * B + j) * kLTaps + (s - 1) * 8 + tap_index(di / s, dj / s);
-                    ffma2(acc[i * B + j], v, w[CL4_DUO_WIDX(k)]);
+                    ffma2(acc[i * B + j], v, w[k]);
                     // sources arrive in row-major order, so taps 3 and 7 are the last uses of their float4: refill it
                     // with the next tile's weights right away (kReload: last item of a tile)
                     if (kReload && (k & 3) == 3) load_weight_group<G>(w, nw, k >> 2);
@@ -158,8 +146,8 @@ __device__ __forceinline__ void duo_b_far(float (&w)[kLW], u64 (&acc)[kLPx], con
                 if (a == 0 && b == 0) continue;
                 const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(sp + (i + 24 * a) * kDPitch + 24 * b);
                 const int k0 = (i * 2) * kLTaps + 16 + tap_index(a, b), k1 = k0 + kLTaps;
-                ffma2(acc[i * 2], v.x, w[CL4_DUO_WIDX_FAR(k0)]);
-                ffma2(acc[i * 2 + 1], v.y, w[CL4_DUO_WIDX_FAR(k1)]);
+                ffma2(acc[i * 2], v.x, w[k0]);
+                ffma2(acc[i * 2 + 1], v.y, w[k1]);
                 if (kReload && (k0 & 3) == 3) {
                     load_weight_group<1>(w, nw, k0 >> 2);
                     load_weight_group<1>(w, nw, k1 >> 2);

@@ -51,10 +51,7 @@ constexpr int kAhead = CL4_SWEEP_AHEAD;  // windows in flight beyond the current
 static_assert(kAhead >= 1 && kAhead < kStages, "prefetch distance");
 constexpr int kProducerTid = CL4_SWEEP_PRODUCER;  // the thread that issues the TMA loads
 constexpr int kStageBytes = kBox * kBox * 4;    // 25600
-#ifndef CL4_EXP_BOXH
-#define CL4_EXP_BOXH kBox  // experiment: load only the first CL4_EXP_BOXH rows of each window (wrong results, timing only)
-#endif
-constexpr int kLoadBytes = kBox * CL4_EXP_BOXH * 4;
+constexpr int kLoadBytes = kBox * kBox * 4;
 constexpr size_t kSweepSmem = (size_t)kStages * kStageBytes + 128;
 
 struct TileCoord {
@@ -156,12 +153,8 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
 #ifdef CL4_SWEEP_DEBUG
         dbg_wait += clock64() - tw0;
 #endif
-#ifdef CL4_EXP_NOLOAD  // experiment: the handshake without the copy
-        mbar_arrive(&full[s]);
-#else
         mbar_arrive_expect_tx(&full[s], kLoadBytes);
         tma_load_3d(stage0 + (size_t)s * (kBox * kBox), &tmap, &full[s], ptc.x0, ptc.y0, ptc.b * C + pc);
-#endif
         ++p_item;
 #if CL4_SWEEP_L2_AHEAD > 0  // pull a window further ahead into L2 (no shared memory needed for it)
         if (p_item + CL4_SWEEP_L2_AHEAD - 1 < total) {
@@ -255,9 +248,7 @@ pamr_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __r
 #ifdef CL4_SWEEP_DEBUG
         const long long tf0 = clock64();
 #endif
-#ifndef CL4_EXP_NOWAITFULL  // experiment: consumers do not wait for the window (racy, timing only)
         mbar_wait(&full[s], (uint32_t)((item / kStages) & 1));
-#endif
 #ifdef CL4_SWEEP_DEBUG
         if (kWS) dbg_wait += clock64() - tf0;
 #endif
@@ -559,7 +550,7 @@ int launch_sweep_tma(const float* w, const float* padded_in, float* out, int out
                      const Dilations& dil, int D, cudaStream_t s) {
     CUtensorMap tmap;
     const int Wp = W + 2 * kHalo, Hp = H + 2 * kHalo;
-    const int rc = encode_tmap_3d_f32(&tmap, padded_in, Wp, Hp, (long long)B * C, kBox, CL4_EXP_BOXH);
+    const int rc = encode_tmap_3d_f32(&tmap, padded_in, Wp, Hp, (long long)B * C, kBox, kBox);
     if (rc != 0) {
         set_error("pamr_sweep_tma: cuTensorMapEncodeTiled failed (%d)", rc);
         return CL4_ECUDA;
