@@ -437,7 +437,8 @@ def time_small_maps(cl4, dev):
     """The regime the trainer really runs PAMR in (train.py:372-385): softmax -> denorm + shrink -> PAMR(10,
     [1,2,4,8,12]) -> label gating -> pseudo_gtmask on feature-resolution maps.  Per shape: microseconds per
     phase1_pseudo_labels call (CUDA events over 50 calls, Python wrapper included), launches per call, and the fused
-    PAMR kernel alone with its roofline (it is launch/latency-bound, not bandwidth-bound: the numbers say so)."""
+    PAMR kernel alone with its roofline (one-tile maps are launch/latency-bound; maps of several tiles are bound by the
+    weight re-reads from L2: the numbers say so)."""
     from cl4wsis_b200.wss import single_stage as ss
     peak, _ = measured_peak_gbs()
     out = []
@@ -455,12 +456,25 @@ def time_small_maps(cl4, dev):
         P, T = 40, 10
         nbytes = 4.0 * h * w * B * (3 + P + 2 * C)            # image + weights + masks in once, out once
         flops = 2.0 * C * P * T * h * w * B
+        tiles = -(-h // 32) * -(-w // 32)
+        extra = {}
+        if tiles == 1:
+            bound = ("launch + on-chip latency (all T sweeps inside one CTA per class group, weights in registers throughout; "
+                     "HBM and FP32 fractions are both small)")
+        else:
+            # a CTA (two classes of one image at C = 81, pamr_fused.cu pick_cpb) walks the map's tiles in every iteration and
+            # re-reads a tile's weights (32 x 32 x P floats) from L2 at every tile switch
+            cpb = 2 if B * -(-C // 2) > 3 * 148 else 1
+            l2 = 4.0 * 1024 * P * tiles * T * B * -(-C // cpb)
+            extra = {"pamr_l2_weight_bytes": l2, "pamr_l2_weight_tbs": l2 / (us_pamr * 1e-6) / 1e12}
+            bound = ("L2 slice throughput + per-item latency at 8 warps per SM: every CTA re-reads a tile's weights from L2 per "
+                     "(tile, iteration) -- pamr_l2_weight_bytes per call against ~12 TB/s of L2; HBM and FP32 fractions are small")
         out.append({"shape": f"B{B} C{C} {h}x{w} D5 T10 (images {Hi}x{Wi}; {note})", "phase1_pseudo_labels_us": us,
                     "launches_per_call": getattr(ss, "PHASE1_LAUNCHES", None), "pamr_call_us": us_pamr,
                     "pamr_launches": 2, "pamr_algorithmic_bytes": nbytes,
                     "pamr_hbm_frac": nbytes / (us_pamr * 1e-6) / 1e9 / peak,
                     "pamr_fp32_frac_of_74.4": flops / (us_pamr * 1e-6) / 74.4e12,
-                    "bound": "launch + on-chip latency (all T sweeps inside one CTA per class group; HBM and FP32 fractions are both small)"})
+                    "bound": bound, **extra})
     return out
 
 

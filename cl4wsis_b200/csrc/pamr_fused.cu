@@ -228,13 +228,16 @@ bool pamr_fused_applicable(int H, int W, const Dilations& dil, int D) {
     return true;
 }
 
-// classes per CTA: as many CTAs as possible up to one wave of the GPU, then the fewest waves
-static int pick_cpb(int B, int C, int cpb_max) {
+// Classes per CTA: the fewest waves x classes per CTA.  On maps of more than one tile a CTA re-reads a tile's weights from L2 at
+// every tile switch, i.e. once per (tile, iteration) whatever its class count, and only part of that hides behind the last class
+// pass: measured as 0.45 of a class pass (B16, 56 x 56: C = 81 667 -> 629 us with two classes per CTA, C = 21 233 -> 260 us;
+// gpurun_out/r03j_cpb.log), so a second class per CTA pays when it costs at most that many extra waves.
+static int pick_cpb(int B, int C, int cpb_max, bool multi_tile) {
     int best = 1;
     long long best_cost = -1;
     for (int cpb = 1; cpb <= cpb_max && cpb <= C; ++cpb) {
         const long long ctas = (long long)B * ceil_div(C, cpb);
-        const long long cost = ((ctas + kNumSMs - 1) / kNumSMs) * cpb;  // waves x classes per CTA
+        const long long cost = ((ctas + kNumSMs - 1) / kNumSMs) * (100 * cpb + (multi_tile ? 45 : 0));
         if (best_cost < 0 || cost < best_cost || (cost == best_cost && cpb > best)) {
             best = cpb;
             best_cost = cost;
@@ -264,7 +267,7 @@ static int launch_fused_one_ep(const float* w, const float* mi, float* mo, int B
     constexpr size_t kPlaneBytes = (size_t)PITCH * PITCH * 4;
     constexpr int kCpbMax = (int)((227 * 1024) / (2 * kPlaneBytes));
     static_assert(kCpbMax >= 1, "plane too large for shared memory");
-    const int cpb = pick_cpb(B, C, kCpbMax);
+    const int cpb = pick_cpb(B, C, kCpbMax, H > kTile || W > kTile);
     const size_t smem = (size_t)cpb * 2 * kPlaneBytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // per device
     if (e != cudaSuccess) {
