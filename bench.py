@@ -462,9 +462,11 @@ def time_small_maps(cl4, dev):
             bound = ("launch + on-chip latency (all T sweeps inside one CTA per class group, weights in registers throughout; "
                      "HBM and FP32 fractions are both small)")
         else:
-            # a CTA (two classes of one image at C = 81, pamr_fused.cu pick_cpb) walks the map's tiles in every iteration and
+            # a CTA (cpb classes of one image: the rule of pamr_fused.cu pick_cpb, restated below) walks the map's tiles in every iteration and
             # re-reads a tile's weights (32 x 32 x P floats) from L2 at every tile switch
-            cpb = 2 if B * -(-C // 2) > 3 * 148 else 1
+            pitch = 64 + 2 * 12                                   # two tiles + a frame of 12 (dilations <= 12)
+            cpb_max = (227 * 1024) // (2 * pitch * pitch * 4)
+            cpb = min(range(1, min(cpb_max, C) + 1), key=lambda k: (-(-(B * -(-C // k)) // 148) * (100 * k + 45), -k))
             l2 = 4.0 * 1024 * P * tiles * T * B * -(-C // cpb)
             extra = {"pamr_l2_weight_bytes": l2, "pamr_l2_weight_tbs": l2 / (us_pamr * 1e-6) / 1e12}
             bound = ("L2 slice throughput + per-item latency at 8 warps per SM: every CTA re-reads a tile's weights from L2 per "

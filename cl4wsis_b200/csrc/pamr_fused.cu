@@ -41,12 +41,20 @@ struct Phase1Epilogue {
     float cutoff_top, cutoff_bkg, cutoff_low;
 };
 
+// plane pitch = map extent (one or two tiles) + 2 x frame
+constexpr int kFusedHaloSmall = 12;
+__host__ __device__ constexpr int fused_pitch(int tiles, int halo) { return tiles * kTile + 2 * halo; }
+__host__ __device__ constexpr int fused_halo(int pitch) {
+    return (pitch == fused_pitch(1, kFusedHaloSmall) || pitch == fused_pitch(2, kFusedHaloSmall)) ? kFusedHaloSmall : kHalo;
+}
+
 template <int D, class DS, int PITCH, bool kP1>
 __global__ void __launch_bounds__(kSweepThreads, 1)
 pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_in, float* __restrict__ mask_out,
                   int C, int H, int W, int cpb, int num_iter, Dilations dil, Phase1Epilogue ep) {
     constexpr int P = 8 * D;
     constexpr int kPlane = PITCH * PITCH;  // PITCH rows of PITCH floats
+    constexpr int HALO = fused_halo(PITCH);  // replicate frame around the map: 24, or 12 when no dilation exceeds 12
     extern __shared__ __align__(16) float smem[];
 
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
@@ -56,7 +64,7 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
     const int c0 = blockIdx.x * cpb;
     const int nc = min(cpb, C - c0);
     const int tiles_x = ceil_div(W, kTile), tiles_y = ceil_div(H, kTile), n_tiles = tiles_x * tiles_y;
-    const int Hp = H + 2 * kHalo, Wp = W + 2 * kHalo;
+    const int Hp = H + 2 * HALO, Wp = W + 2 * HALO;
     const size_t HW = (size_t)H * W;
 
     // planes: [class][ping-pong][PITCH][PITCH]
@@ -68,9 +76,9 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
         const float* src = mask_in + ((size_t)b * C + c0 + c) * HW;
         float* dst = plane(c, 0);
         for (int py = wrp; py < Hp; py += kSweepThreads / 32) {
-            const float* srow = src + (size_t)clampi(py - kHalo, 0, H - 1) * W;
+            const float* srow = src + (size_t)clampi(py - HALO, 0, H - 1) * W;
             float* drow = dst + py * PITCH;
-            for (int px = lane; px < Wp; px += 32) drow[px] = __ldg(srow + clampi(px - kHalo, 0, W - 1));
+            for (int px = lane; px < Wp; px += 32) drow[px] = __ldg(srow + clampi(px - HALO, 0, W - 1));
         }
     }
 
@@ -107,7 +115,7 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
         for (int t = 0; t < n_tiles; ++t) {
             const int tyi = t / tiles_x;
             const int y0 = tyi * kTile, x0 = (t - tyi * tiles_x) * kTile;
-            const int sbase = (y0 + ty + kHalo) * PITCH + (x0 + tx + kHalo);
+            const int sbase = (y0 + ty + HALO) * PITCH + (x0 + tx + HALO);
             const int x = x0 + tx;
             unsigned valid = 0u;
 #pragma unroll
@@ -162,19 +170,19 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
         for (int c = 0; c < nc; ++c) {
             float* pl = plane(c, nxt);
             // rows above and below the image: full padded width
-            for (int r = wrp; r < 2 * kHalo; r += kSweepThreads / 32) {
-                const int py = (r < kHalo) ? r : (H + r);
-                const float* srow = pl + ((r < kHalo) ? kHalo : (H + kHalo - 1)) * PITCH;
+            for (int r = wrp; r < 2 * HALO; r += kSweepThreads / 32) {
+                const int py = (r < HALO) ? r : (H + r);
+                const float* srow = pl + ((r < HALO) ? HALO : (H + HALO - 1)) * PITCH;
                 float* drow = pl + py * PITCH;
-                for (int px = lane; px < Wp; px += 32) drow[px] = srow[clampi(px, kHalo, W + kHalo - 1)];
+                for (int px = lane; px < Wp; px += 32) drow[px] = srow[clampi(px, HALO, W + HALO - 1)];
             }
             // left and right bands of the image rows: lanes 0..23 left, the next 24 right
             for (int r = wrp; r < H; r += kSweepThreads / 32) {
-                float* row = pl + (r + kHalo) * PITCH;
-                const float vl = row[kHalo], vr = row[W + kHalo - 1];
-                if (lane < kHalo) {
+                float* row = pl + (r + HALO) * PITCH;
+                const float vl = row[HALO], vr = row[W + HALO - 1];
+                if (lane < HALO) {
                     row[lane] = vl;
-                    row[W + kHalo + lane] = vr;
+                    row[W + HALO + lane] = vr;
                 }
             }
         }
@@ -197,7 +205,7 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
         int* cnt = ep.cnt + (size_t)b * HW;
         const int fin = (num_iter & 1);  // the plane the last iteration wrote: nxt of it = num_iter - 1
         for (int c = 0; c < nc; ++c) {
-            const float* gm = plane(c, fin) + kHalo * PITCH + kHalo;
+            const float* gm = plane(c, fin) + HALO * PITCH + HALO;
             float* po = ep.pseudo + ((size_t)b * C + c0 + c) * HW;
             const float th = s_thr[c];
             for (int y = wrp; y < H; y += kSweepThreads / 32)
@@ -310,8 +318,17 @@ static int launch_fused_P(const float* w, const float* mi, float* mo, int B, int
 // w: tile-major weights; mask_in / mask_out: plain [B*C][H][W]; num_iter >= 1
 int launch_pamr_fused(const float* w, const float* mask_in, float* mask_out, int B, int C, int H, int W, int num_iter,
                       const Dilations& dil, int D, cudaStream_t s) {
-    if (H <= kTile && W <= kTile) return launch_fused_P<kBox>(w, mask_in, mask_out, B, C, H, W, num_iter, dil, D, s);
-    return launch_fused_P<2 * kTile + 2 * kHalo>(w, mask_in, mask_out, B, C, H, W, num_iter, dil, D, s);
+    // the trainer's dilation set [1,2,4,8,12] (train.py:81) needs a frame of 12, not 24: planes of 56^2 / 88^2 instead of 80^2 / 112^2
+    // floats -- less frame to rewrite per iteration and room for three classes per CTA on two-tile maps
+    bool small = true;
+    for (int i = 0; i < D; ++i) small = small && dil.d[i] <= kFusedHaloSmall;
+    const bool one = H <= kTile && W <= kTile;
+    if (small) {
+        if (one) return launch_fused_P<fused_pitch(1, kFusedHaloSmall)>(w, mask_in, mask_out, B, C, H, W, num_iter, dil, D, s);
+        return launch_fused_P<fused_pitch(2, kFusedHaloSmall)>(w, mask_in, mask_out, B, C, H, W, num_iter, dil, D, s);
+    }
+    if (one) return launch_fused_P<fused_pitch(1, kHalo)>(w, mask_in, mask_out, B, C, H, W, num_iter, dil, D, s);
+    return launch_fused_P<fused_pitch(2, kHalo)>(w, mask_in, mask_out, B, C, H, W, num_iter, dil, D, s);
 }
 
 // The same launch with the phase-1 epilogue: mask_out receives the label-gated masks, pseudo / thr as Phase1Epilogue says.
