@@ -41,6 +41,47 @@ struct Phase1Epilogue {
     float cutoff_top, cutoff_bkg, cutoff_low;
 };
 
+// Pixels per thread.  The 4-pixel mapping of the HBM-resident sweep (8 warps per CTA) leaves an on-chip CTA latency-bound:
+// its four pixels share no source, so two pixels per thread on 16 warps cost the same LDS and FFMA and hide twice the latency.
+#ifndef CL4_FUSED_PX
+#define CL4_FUSED_PX 2
+#endif
+constexpr int kFusedPx = CL4_FUSED_PX;                     // rows ty + 4*i, i < kFusedPx
+constexpr int kFusedThreads = (kTile / kFusedPx) * 32;     // 512 (256 with four pixels per thread)
+static_assert(kFusedPx == 2 || kFusedPx == 4, "pixels per thread");
+
+// One class of one tile (sweep_class of pamr_sweep.cuh with kFusedPx pixels per thread).  kReload: refill the weight registers with
+// the next tile's weights right after their last use.
+template <int D, class DS, bool kReload, int PITCH>
+__device__ __forceinline__ void fused_class(float (&w)[kFusedPx][8 * D], const float* __restrict__ sp, const Dilations& dil,
+                                            const float4* __restrict__ nw, float (&acc)[kFusedPx]) {
+#pragma unroll
+    for (int i = 0; i < kFusedPx; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int g = 0; g < 2 * D; ++g) {  // groups of four taps
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int p = 4 * g + q, di = p >> 3, j = p & 7;
+            const int d = DS::kStatic ? DS::get(di) : dil.d[di];
+            const int dy = (j < 3) ? -1 : ((j < 5) ? 0 : 1);
+            const int dx = (j < 3) ? (j - 1) : ((j == 3) ? -1 : ((j == 4) ? 1 : (j - 6)));
+            const int off = dy * d * PITCH + dx * d;
+#pragma unroll
+            for (int i = 0; i < kFusedPx; ++i) acc[i] = fmaf(w[i][p], sp[off + i * kRowGap * PITCH], acc[i]);
+        }
+        if (kReload) {
+#pragma unroll
+            for (int i = 0; i < kFusedPx; ++i) {
+                const float4 v = __ldg(nw + g * (kTile * kTile) + i * kRowGap * kTile);
+                w[i][4 * g + 0] = v.x;
+                w[i][4 * g + 1] = v.y;
+                w[i][4 * g + 2] = v.z;
+                w[i][4 * g + 3] = v.w;
+            }
+        }
+    }
+}
+
 // plane pitch = map extent (one or two tiles) + 2 x frame
 constexpr int kFusedHaloSmall = 12;
 __host__ __device__ constexpr int fused_pitch(int tiles, int halo) { return tiles * kTile + 2 * halo; }
@@ -49,7 +90,7 @@ __host__ __device__ constexpr int fused_halo(int pitch) {
 }
 
 template <int D, class DS, int PITCH, bool kP1>
-__global__ void __launch_bounds__(kSweepThreads, 1)
+__global__ void __launch_bounds__(kFusedThreads, 1)
 pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_in, float* __restrict__ mask_out,
                   int C, int H, int W, int cpb, int num_iter, Dilations dil, Phase1Epilogue ep) {
     constexpr int P = 8 * D;
@@ -59,7 +100,7 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
 
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int tx = lane;
-    const int ty = (wrp >> 2) * 16 + (wrp & 3);  // rows ty + 4*i
+    const int ty = (wrp >> 2) * (kRowGap * kFusedPx) + (wrp & 3);  // rows ty + 4*i, i < kFusedPx
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * cpb;
     const int nc = min(cpb, C - c0);
@@ -75,7 +116,7 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
     for (int c = 0; c < nc; ++c) {
         const float* src = mask_in + ((size_t)b * C + c0 + c) * HW;
         float* dst = plane(c, 0);
-        for (int py = wrp; py < Hp; py += kSweepThreads / 32) {
+        for (int py = wrp; py < Hp; py += kFusedThreads / 32) {
             const float* srow = src + (size_t)clampi(py - HALO, 0, H - 1) * W;
             float* drow = dst + py * PITCH;
             for (int px = lane; px < Wp; px += 32) drow[px] = __ldg(srow + clampi(px - HALO, 0, W - 1));
@@ -86,13 +127,13 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
     auto weight_ptr = [&](int t) -> const float4* {
         return reinterpret_cast<const float4*>(wts) + ((size_t)b * n_tiles + t) * (P / 4 * kTile * kTile) + ty * kTile + tx;
     };
-    float w[kPx][P];
+    float w[kFusedPx][P];
     {
         const float4* wp = weight_ptr(0);
 #pragma unroll
         for (int g = 0; g < P / 4; ++g)
 #pragma unroll
-            for (int i = 0; i < kPx; ++i) {
+            for (int i = 0; i < kFusedPx; ++i) {
                 const float4 v = __ldg(wp + g * (kTile * kTile) + i * kRowGap * kTile);
                 w[i][4 * g + 0] = v.x;
                 w[i][4 * g + 1] = v.y;
@@ -103,12 +144,12 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
     __syncthreads();
 
     constexpr int kCpbCap = (227 * 1024) / (2 * kPlane * 4);   // classes per CTA that fit (launch_fused_one)
-    __shared__ float s_cmax[kP1 ? kCpbCap * (kSweepThreads / 32) : 1];  // running plane maxima, one slot per (class, warp)
+    __shared__ float s_cmax[kP1 ? kCpbCap * (kFusedThreads / 32) : 1];  // running plane maxima, one slot per (class, warp)
     __shared__ int s_last;
     if (kP1)
-        for (int i = tid; i < kCpbCap * (kSweepThreads / 32); i += kSweepThreads) s_cmax[i] = -INFINITY;
+        for (int i = tid; i < kCpbCap * (kFusedThreads / 32); i += kFusedThreads) s_cmax[i] = -INFINITY;
 
-    float acc[kPx];
+    float acc[kFusedPx];
     for (int it = 0; it < num_iter; ++it) {
         const int cur = it & 1, nxt = cur ^ 1;
         const bool last_it = (it == num_iter - 1);
@@ -119,7 +160,7 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
             const int x = x0 + tx;
             unsigned valid = 0u;
 #pragma unroll
-            for (int i = 0; i < kPx; ++i)
+            for (int i = 0; i < kFusedPx; ++i)
                 if (x < W && y0 + ty + i * kRowGap < H) valid |= 1u << i;
             // weights of the tile that follows (this iteration's next tile, or tile 0 of the next iteration)
             const int tn = (t + 1 == n_tiles) ? 0 : t + 1;
@@ -127,9 +168,9 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
             for (int c = 0; c < nc; ++c) {
                 const float* sp = plane(c, cur) + sbase;
                 if (more && c == nc - 1)
-                    sweep_class<D, DS, true, PITCH>(w, sp, dil, weight_ptr(tn), acc);
+                    fused_class<D, DS, true, PITCH>(w, sp, dil, weight_ptr(tn), acc);
                 else
-                    sweep_class<D, DS, false, PITCH>(w, sp, dil, nullptr, acc);
+                    fused_class<D, DS, false, PITCH>(w, sp, dil, nullptr, acc);
                 if (last_it) {
                     float* o = mask_out + ((size_t)b * C + c0 + c) * HW + (size_t)(y0 + ty) * W + x;
                     if (kP1) {
@@ -137,28 +178,28 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
                         const float g = (ep.labels && cls > 0) ? __ldg(ep.labels + (size_t)b * (C - 1) + (cls - 1)) : 1.f;
                         float m = -INFINITY;
 #pragma unroll
-                        for (int i = 0; i < kPx; ++i) {
+                        for (int i = 0; i < kFusedPx; ++i) {
                             if (ep.labels && cls > 0) acc[i] = __fmul_rn(acc[i], g);
                             if ((valid >> i) & 1u) m = nanmax(m, acc[i]);  // torch.max propagates NaN
                         }
 #pragma unroll
                         for (int sft = 16; sft > 0; sft >>= 1) m = nanmax(m, __shfl_xor_sync(0xffffffffu, m, sft));
-                        if (lane == 0) s_cmax[c * (kSweepThreads / 32) + wrp] = nanmax(s_cmax[c * (kSweepThreads / 32) + wrp], m);
+                        if (lane == 0) s_cmax[c * (kFusedThreads / 32) + wrp] = nanmax(s_cmax[c * (kFusedThreads / 32) + wrp], m);
                     }
 #pragma unroll
-                    for (int i = 0; i < kPx; ++i)
+                    for (int i = 0; i < kFusedPx; ++i)
                         if ((valid >> i) & 1u) o[(size_t)(i * kRowGap) * W] = acc[i];
                     if (kP1) {  // the epilogue compares the gated values with the plane's threshold: keep them on-chip (the other
                                 // ping-pong plane is free in the last iteration)
                         float* o2 = plane(c, nxt) + sbase;
 #pragma unroll
-                        for (int i = 0; i < kPx; ++i)
+                        for (int i = 0; i < kFusedPx; ++i)
                             if ((valid >> i) & 1u) o2[i * kRowGap * PITCH] = acc[i];
                     }
                 } else {
                     float* o = plane(c, nxt) + sbase;
 #pragma unroll
-                    for (int i = 0; i < kPx; ++i)
+                    for (int i = 0; i < kFusedPx; ++i)
                         if ((valid >> i) & 1u) o[i * kRowGap * PITCH] = acc[i];
                 }
             }
@@ -170,14 +211,14 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
         for (int c = 0; c < nc; ++c) {
             float* pl = plane(c, nxt);
             // rows above and below the image: full padded width
-            for (int r = wrp; r < 2 * HALO; r += kSweepThreads / 32) {
+            for (int r = wrp; r < 2 * HALO; r += kFusedThreads / 32) {
                 const int py = (r < HALO) ? r : (H + r);
                 const float* srow = pl + ((r < HALO) ? HALO : (H + HALO - 1)) * PITCH;
                 float* drow = pl + py * PITCH;
                 for (int px = lane; px < Wp; px += 32) drow[px] = srow[clampi(px, HALO, W + HALO - 1)];
             }
             // left and right bands of the image rows: lanes 0..23 left, the next 24 right
-            for (int r = wrp; r < H; r += kSweepThreads / 32) {
+            for (int r = wrp; r < H; r += kFusedThreads / 32) {
                 float* row = pl + (r + HALO) * PITCH;
                 const float vl = row[HALO], vr = row[W + HALO - 1];
                 if (lane < HALO) {
@@ -193,8 +234,8 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
         __shared__ float s_thr[kCpbCap];
         __syncthreads();  // s_cmax complete; this CTA's gated planes are visible to the whole CTA
         if (tid < nc) {
-            float mx = s_cmax[tid * (kSweepThreads / 32)];
-            for (int wi = 1; wi < kSweepThreads / 32; ++wi) mx = nanmax(mx, s_cmax[tid * (kSweepThreads / 32) + wi]);
+            float mx = s_cmax[tid * (kFusedThreads / 32)];
+            for (int wi = 1; wi < kFusedThreads / 32; ++wi) mx = nanmax(mx, s_cmax[tid * (kFusedThreads / 32) + wi]);
             const int cls = c0 + tid;
             const float scaled = __fmul_rn(mx, cls == 0 ? ep.cutoff_bkg : ep.cutoff_top);  // mask_max[:, :1] *= bkg; [:, 1:] *= top
             const float th = (ep.cutoff_low > scaled || ep.cutoff_low != ep.cutoff_low) ? ep.cutoff_low : scaled;
@@ -208,7 +249,7 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
             const float* gm = plane(c, fin) + HALO * PITCH + HALO;
             float* po = ep.pseudo + ((size_t)b * C + c0 + c) * HW;
             const float th = s_thr[c];
-            for (int y = wrp; y < H; y += kSweepThreads / 32)
+            for (int y = wrp; y < H; y += kFusedThreads / 32)
                 for (int x = lane; x < W; x += 32) {
                     const bool on = gm[y * PITCH + x] > th;
                     po[(size_t)y * W + x] = on ? 1.f : 0.f;
@@ -222,7 +263,7 @@ pamr_fused_kernel(const float* __restrict__ wts, const float* __restrict__ mask_
         if (s_last) {
             __threadfence();
             float* po = ep.pseudo + (size_t)b * C * HW;
-            for (int i = tid; i < (int)HW; i += kSweepThreads)
+            for (int i = tid; i < (int)HW; i += kFusedThreads)
                 if (__ldcg(cnt + i) > 1)  // ambiguous=True (train.py:384): a pixel claimed by several classes belongs to none
                     for (int c = 0; c < C; ++c) po[(size_t)c * HW + i] = 0.f;
         }
@@ -283,7 +324,7 @@ static int launch_fused_one_ep(const float* w, const float* mi, float* mo, int B
         return CL4_ECUDA;
     }
     dim3 grid(ceil_div(C, cpb), B);
-    kern<<<grid, kSweepThreads, smem, s>>>(w, mi, mo, C, H, W, cpb, num_iter, dil, kP1 ? *t_ep : Phase1Epilogue{});
+    kern<<<grid, kFusedThreads, smem, s>>>(w, mi, mo, C, H, W, cpb, num_iter, dil, kP1 ? *t_ep : Phase1Epilogue{});
     return check_launch("pamr_fused");
 }
 
