@@ -102,6 +102,10 @@ def test_pamr_oracle_random(cl4, oracle, B, C, H, W, dil, T):
     (2, 4, 33, 20, [1, 2, 4, 8, 12, 24], 2),     # two tile rows, one column, W % 4 == 0
     (1, 3, 40, 36, [2, 5, 24], 3),               # runtime dilation offsets
     (1, 2, 32, 64, [1, 2, 4, 8, 12, 24], 1),     # single iteration: straight to the output
+    (2, 5, 57, 64, [1, 2, 4, 8, 12], 3),         # frame of 12 (no dilation above 12): partial second tile row, odd class count
+    (1, 7, 64, 33, [12], 4),                     # frame of 12, runtime dilation offsets, one pixel column in the second tile
+    (1, 2, 33, 33, [5, 12], 3),                  # frame of 12, 2 x 2 tiles of which three hold one row / column
+    (1, 3, 48, 40, [13], 2),                     # one above the small frame: back to the frame of 24
 ])
 def test_pamr_small_map_paths_agree(cl4, oracle, monkeypatch, path, B, C, H, W, dil, T):
     """The three sweep implementations (all iterations on-chip / TMA-staged / register-L1) on the
