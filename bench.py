@@ -469,8 +469,9 @@ def time_small_maps(cl4, dev):
             cpb = min(range(1, min(cpb_max, C) + 1), key=lambda k: (-(-(B * -(-C // k)) // 148) * (100 * k + 45), -k))
             l2 = 4.0 * 1024 * P * tiles * T * B * -(-C // cpb)
             extra = {"pamr_l2_weight_bytes": l2, "pamr_l2_weight_tbs": l2 / (us_pamr * 1e-6) / 1e12}
-            bound = ("L2 slice throughput + per-item latency at 8 warps per SM: every CTA re-reads a tile's weights from L2 per "
-                     "(tile, iteration) -- pamr_l2_weight_bytes per call against ~12 TB/s of L2; HBM and FP32 fractions are small")
+            bound = ("shared-memory pipe (l1tex 76 %, profiles/r03c_fused_ncu_summary.txt: one LDS.32 wavefront per 32 FMAs, no source "
+                     "reuse in this mapping) on top of the weight re-reads from L2 -- a tile's weights per (tile, iteration, CTA): "
+                     "pamr_l2_weight_bytes per call; HBM and FP32 fractions are small")
         out.append({"shape": f"B{B} C{C} {h}x{w} D5 T10 (images {Hi}x{Wi}; {note})", "phase1_pseudo_labels_us": us,
                     "launches_per_call": getattr(ss, "PHASE1_LAUNCHES", None), "pamr_call_us": us_pamr,
                     "pamr_launches": 2, "pamr_algorithmic_bytes": nbytes,
