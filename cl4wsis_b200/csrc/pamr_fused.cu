@@ -5,15 +5,18 @@
 // One CTA owns `cpb` classes of one image for all iterations.  Classes are independent in PAMR
 // (they only share the affinity weights), so CTAs never communicate.  Per class the CTA keeps two
 // replicate-padded planes (ping-pong) in shared memory: the clamped neighbour of wss/modules.py:57
-// is an ordinary in-bounds LDS at an immediate offset, exactly as in the HBM-resident TMA sweep
-// (pamr_tma.cu), whose inner loop (sweep_class) and thread mapping this kernel shares:
-//   * a thread owns 4 pixels of one column, 4 rows apart, of a 32 x 32 tile and keeps their
-//     4 x 8D weights in registers for all classes and — when the map is one tile — all iterations;
+// is an ordinary in-bounds LDS at an immediate offset, as in the HBM-resident 4-pixel sweep (pamr_tma.cu),
+// whose tile-major weight layout this kernel reads:
+//   * a thread owns 2 pixels of one column, 4 rows apart, of a 32 x 32 tile (16 warps per CTA) and keeps their
+//     2 x 8D weights in registers for all classes and — when the map is one tile — all iterations;
 //   * maps of 2-4 tiles re-read the tile-major weights from L2 at each tile switch, software-
 //     pipelined into the last class pass of the previous tile;
-//   * after each iteration the 24-pixel frame of the new planes is rewritten from their interior.
+//   * the frame around the map is 12 pixels when no dilation exceeds 12 (the trainer's set, train.py:81), else 24;
+//     after each iteration the frame of the new planes is rewritten from their interior.
 // HBM traffic is the minimum: masks in once, masks out once, weights once per CTA (L2 hits after the
-// first CTA of an image).  The bound is shared-memory bandwidth (143 LDS per 192 FFMA).
+// first CTA of an image).  The bound is the shared-memory pipe (one LDS.32 wavefront per 32 FMAs; ptxas shares the ~10 of 80
+// sources per class that the two pixels have in common) and, on multi-tile maps, the weight re-reads from L2
+// (profiles/r02_notes.md sections 11, 12; profiles/r03c_fused_ncu_summary.txt).
 #include "common.cuh"
 #include "pamr_internal.cuh"
 #include "pamr_sweep.cuh"
